@@ -1,0 +1,115 @@
+/*
+ * o3d_b200.h — C ABI of libo3d_b200.so (hand-written sm_100a kernels for the Open3DSOT hot path).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`; the caller owns all buffers,
+ *     including scratch and pre-zeroed gradient outputs — nothing is allocated inside;
+ *   - float = IEEE fp32, indices = int32, tensors dense row-major in the shape given in the comment;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are only enqueued (no synchronisation, no
+ *     host-side state), so every entry point may be captured into a CUDA graph;
+ *   - return value 0 = ok, <0 = argument / CUDA error; o3d_last_error() gives the text (thread-local);
+ *   - no torch types anywhere.
+ *
+ * The first block mirrors, one to one, the nine pybind entry points of `pointnet2_ops._ext` that the
+ * reference binds at pointnet2/utils/pointnet2_utils.py:17 and calls at :56,:92,:98,:125,:162,:184,:217,
+ * :237,:268 (tensor layouts and result conventions identical).  The second block holds the fused
+ * supersets used by the B200-native modules (channels-last activations).
+ */
+#ifndef O3D_B200_H
+#define O3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O3D_B200_VERSION 100
+
+int o3d_version(void);
+const char* o3d_last_error(void);
+int o3d_opt_threads(int work);  /* upstream cuda_utils.h opt_n_threads(): defines the FPS tie order */
+int o3d_device_sms(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block 1 — drop-in for pointnet2_ops._ext
+ * ---------------------------------------------------------------------------------------------- */
+
+/* _ext.furthest_point_sampling(xyz, npoint)            pointnet2_utils.py:56
+ * xyz (B,N,3) f32 -> idx (B,npoint) i32. Starts at index 0, skips points with |p|^2 <= 1e-3,
+ * ties resolved exactly as the upstream block reduction does.  N <= 16384.                      */
+int o3d_fps(const float* xyz, int B, int N, int npoint, int32_t* idx, void* stream);
+
+/* _ext.gather_points(features, idx)                    pointnet2_utils.py:92
+ * features (B,C,N), idx (B,M) -> out (B,C,M)                                                    */
+int o3d_gather(const float* features, const int32_t* idx, int B, int C, int N, int M, float* out, void* stream);
+
+/* _ext.gather_points_grad(grad_out, idx, N)            pointnet2_utils.py:98
+ * grad_out (B,C,M), idx (B,M) -> grad_features (B,C,N), MUST be zero-filled by the caller       */
+int o3d_gather_grad(const float* grad_out, const int32_t* idx, int B, int C, int N, int M, float* grad_features,
+                    void* stream);
+
+/* _ext.ball_query(new_xyz, xyz, radius, nsample)       pointnet2_utils.py:268
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample): first nsample indices in ascending order with
+ * d^2 < radius^2 (strict, fp32), remaining slots = first hit, no hit = 0.                        */
+int o3d_ball_query(const float* new_xyz, const float* xyz, int B, int N, int M, float radius, int nsample,
+                   int32_t* idx, void* stream);
+
+/* _ext.group_points(features, idx)                     pointnet2_utils.py:217
+ * features (B,C,N), idx (B,M,S) -> out (B,C,M,S)                                                */
+int o3d_group(const float* features, const int32_t* idx, int B, int C, int N, int M, int S, float* out, void* stream);
+
+/* _ext.group_points_grad(grad_out, idx, N)             pointnet2_utils.py:237
+ * grad_out (B,C,M,S), idx (B,M,S) -> grad_features (B,C,N), zero-filled by the caller           */
+int o3d_group_grad(const float* grad_out, const int32_t* idx, int B, int C, int N, int M, int S, float* grad_features,
+                   void* stream);
+
+/* _ext.three_nn(unknown, known)                        pointnet2_utils.py:125
+ * unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) SQUARED distances, idx (B,n,3); ties -> lower index;
+ * m < 3 leaves +inf / 0 in the unused slots (upstream 1e40 cast to float).                      */
+int o3d_three_nn(const float* unknown, const float* known, int B, int n, int m, float* dist2, int32_t* idx,
+                 void* stream);
+
+/* _ext.three_interpolate(features, idx, weight)        pointnet2_utils.py:162
+ * features (B,c,m), idx (B,n,3), weight (B,n,3) -> out (B,c,n)                                   */
+int o3d_three_interpolate(const float* features, const int32_t* idx, const float* weight, int B, int c, int m, int n,
+                          float* out, void* stream);
+
+/* _ext.three_interpolate_grad(grad_out, idx, weight, m) pointnet2_utils.py:184
+ * grad_out (B,c,n) -> grad_features (B,c,m), zero-filled by the caller                          */
+int o3d_three_interpolate_grad(const float* grad_out, const int32_t* idx, const float* weight, int B, int c, int n,
+                               int m, float* grad_features, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block 2 — fused supersets (channels-last activations: a feature tensor is (B, N, C), so one
+ * point's channel vector is one contiguous, 16-byte-aligned row; C % 4 == 0)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* QueryAndGroup.forward in one kernel (pointnet2_utils.py:299-339): ball query + xyz grouping +
+ * centre subtraction (+ /radius) + feature grouping + concat.
+ *   xyz (B,N,3), new_xyz (B,M,3), feat_cl (B,N,C) or NULL (C=0)
+ *   -> idx (B,M,S) (may be NULL), grouped_cl (B,M,S,C+4): [features(C) | dx dy dz | 0]
+ * (the reference's channel order [xyz, features] is restored by the weight packing of the MLP).  */
+int o3d_ballquery_group(const float* xyz, const float* new_xyz, const float* feat_cl, int B, int N, int M, int C,
+                        float radius, int nsample, int normalize_xyz, int32_t* idx, float* grouped_cl, void* stream);
+
+/* Backward of the grouping above w.r.t. features and (optionally) coordinates.
+ *   grad_grouped_cl (B,M,S,C+4), idx (B,M,S)
+ *   -> grad_feat_cl (B,N,C) += ..., grad_xyz (B,N,3) += ..., grad_new_xyz (B,M,3) -= sum_s ...
+ * all three accumulated with fp32 reductions (pre-zeroed by caller; any may be NULL).            */
+int o3d_ballquery_group_grad(const float* grad_grouped_cl, const int32_t* idx, int B, int N, int M, int C, int S,
+                             float radius, int normalize_xyz, float* grad_feat_cl, float* grad_xyz,
+                             float* grad_new_xyz, void* stream);
+
+/* PointnetFPModule's three_nn + inverse-distance weights + three_interpolate in one kernel
+ * (pointnet2_modules.py:187-195): unknown (B,n,3), known (B,m,3), known_feat_cl (B,m,c)
+ *   -> out_cl (B,n,c), idx (B,n,3), weight (B,n,3)  (idx/weight kept for the backward)            */
+int o3d_three_nn_interpolate(const float* unknown, const float* known, const float* known_feat_cl, int B, int n, int m,
+                             int c, float* out_cl, int32_t* idx, float* weight, void* stream);
+int o3d_three_nn_interpolate_grad(const float* grad_out_cl, const int32_t* idx, const float* weight, int B, int n, int m,
+                                  int c, float* grad_known_feat_cl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* O3D_B200_H */

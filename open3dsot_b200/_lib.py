@@ -1,0 +1,61 @@
+"""ctypes binding of libo3d_b200.so (the C ABI declared in include/o3d_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a kernel reports an error, a
+RuntimeError is raised.  Build with `python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libo3d_b200.so")
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/o3d_b200.h
+PROTOTYPES = {
+    "o3d_version": [],
+    "o3d_last_error": [],
+    "o3d_opt_threads": [_i],
+    "o3d_device_sms": [],
+    "o3d_fps": [_p, _i, _i, _i, _p, _p],
+    "o3d_gather": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "o3d_gather_grad": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "o3d_ball_query": [_p, _p, _i, _i, _i, _f, _i, _p, _p],
+    "o3d_group": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "o3d_group_grad": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "o3d_three_nn": [_p, _p, _i, _i, _i, _p, _p, _p],
+    "o3d_three_interpolate": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "o3d_three_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "o3d_ballquery_group": [_p, _p, _p, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p],
+    "o3d_ballquery_group_grad": [_p, _p, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p],
+    "o3d_three_nn_interpolate": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "o3d_three_nn_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+}
+_RESTYPE = {"o3d_last_error": ctypes.c_char_p}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CDLL; raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"open3dsot_b200: native library not found at {LIB_PATH}. There is no CPU or PyTorch fallback; "
+                "build it with `python -c \"import __graft_entry__ as g; g.build()\"` (needs nvcc).")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the .so is stale -> rebuild
+            fn.argtypes = args
+            fn.restype = _RESTYPE.get(name, ctypes.c_int)
+        _lib = L
+    return _lib
+
+
+def check(status, name):
+    if status != 0:
+        msg = lib().o3d_last_error()
+        raise RuntimeError(f"{name} failed with status {status}: {msg.decode() if msg else ''}")

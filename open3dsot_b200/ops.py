@@ -1,0 +1,171 @@
+"""Tensor-level entry points: torch tensors in, C-ABI calls on the current CUDA stream, torch tensors out.
+
+torch is used for device memory and the stream only.  Argument checks follow upstream `pointnet2_ops`
+(CHECK_CONTIGUOUS / CHECK_IS_FLOAT / CHECK_IS_INT / CHECK_CUDA -> RuntimeError; "CPU not supported").
+"""
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_f(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (CPU not supported)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be a float tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+
+
+def _chk_i(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (CPU not supported)")
+    if t.dtype != torch.int32:
+        raise RuntimeError(f"{name} must be an int tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+
+
+def _call(name, *args):
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+# ------------------------------------------------------------------ the nine `_ext` entry points
+def furthest_point_sampling(xyz, npoint):
+    _chk_f(xyz, "xyz")
+    B, N, _ = xyz.shape
+    out = torch.empty(B, npoint, dtype=torch.int32, device=xyz.device)
+    _call("o3d_fps", xyz.data_ptr(), B, N, int(npoint), out.data_ptr(), _stream())
+    return out
+
+
+def gather_points(features, idx):
+    _chk_f(features, "features"); _chk_i(idx, "idx")
+    B, C, N = features.shape
+    M = idx.shape[1]
+    out = torch.empty(B, C, M, dtype=torch.float32, device=features.device)
+    _call("o3d_gather", features.data_ptr(), idx.data_ptr(), B, C, N, M, out.data_ptr(), _stream())
+    return out
+
+
+def gather_points_grad(grad_out, idx, N):
+    _chk_f(grad_out, "grad_out"); _chk_i(idx, "idx")
+    B, C, M = grad_out.shape
+    out = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+    _call("o3d_gather_grad", grad_out.data_ptr(), idx.data_ptr(), B, C, int(N), M, out.data_ptr(), _stream())
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    _chk_f(new_xyz, "new_xyz"); _chk_f(xyz, "xyz")
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    out = torch.empty(B, M, nsample, dtype=torch.int32, device=xyz.device)
+    _call("o3d_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), B, N, M, float(radius), int(nsample), out.data_ptr(),
+          _stream())
+    return out
+
+
+def group_points(features, idx):
+    _chk_f(features, "features"); _chk_i(idx, "idx")
+    B, C, N = features.shape
+    _, M, S = idx.shape
+    out = torch.empty(B, C, M, S, dtype=torch.float32, device=features.device)
+    _call("o3d_group", features.data_ptr(), idx.data_ptr(), B, C, N, M, S, out.data_ptr(), _stream())
+    return out
+
+
+def group_points_grad(grad_out, idx, N):
+    _chk_f(grad_out, "grad_out"); _chk_i(idx, "idx")
+    B, C, M, S = grad_out.shape
+    out = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+    _call("o3d_group_grad", grad_out.data_ptr(), idx.data_ptr(), B, C, int(N), M, S, out.data_ptr(), _stream())
+    return out
+
+
+def three_nn(unknown, known):
+    _chk_f(unknown, "unknown"); _chk_f(known, "known")
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
+    idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
+    _call("o3d_three_nn", unknown.data_ptr(), known.data_ptr(), B, n, m, dist2.data_ptr(), idx.data_ptr(), _stream())
+    return dist2, idx
+
+
+def three_interpolate(features, idx, weight):
+    _chk_f(features, "features"); _chk_i(idx, "idx"); _chk_f(weight, "weight")
+    B, c, m = features.shape
+    n = idx.shape[1]
+    out = torch.empty(B, c, n, dtype=torch.float32, device=features.device)
+    _call("o3d_three_interpolate", features.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, c, m, n, out.data_ptr(),
+          _stream())
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    _chk_f(grad_out, "grad_out"); _chk_i(idx, "idx"); _chk_f(weight, "weight")
+    B, c, n = grad_out.shape
+    out = torch.zeros(B, c, int(m), dtype=torch.float32, device=grad_out.device)
+    _call("o3d_three_interpolate_grad", grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, c, n, int(m),
+          out.data_ptr(), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ fused supersets (channels-last)
+def ballquery_group(xyz, new_xyz, feat_cl, radius, nsample, normalize_xyz=False, return_idx=True):
+    """xyz (B,N,3), new_xyz (B,M,3), feat_cl (B,N,C)|None -> grouped (B,M,S,C+4) [feat | dx dy dz 0], idx (B,M,S)."""
+    _chk_f(xyz, "xyz"); _chk_f(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    C = 0
+    if feat_cl is not None:
+        _chk_f(feat_cl, "feat_cl")
+        C = feat_cl.shape[2]
+    grouped = torch.empty(B, M, nsample, C + 4, dtype=torch.float32, device=xyz.device)
+    idx = torch.empty(B, M, nsample, dtype=torch.int32, device=xyz.device) if return_idx else None
+    _call("o3d_ballquery_group", xyz.data_ptr(), new_xyz.data_ptr(), feat_cl.data_ptr() if C else None, B, N, M, C,
+          float(radius), int(nsample), int(bool(normalize_xyz)), idx.data_ptr() if return_idx else None,
+          grouped.data_ptr(), _stream())
+    return grouped, idx
+
+
+def ballquery_group_grad(grad_grouped, idx, N, radius, normalize_xyz, need_feat=True, need_xyz=False,
+                         need_new_xyz=False):
+    _chk_f(grad_grouped, "grad_grouped"); _chk_i(idx, "idx")
+    B, M, S, row = grad_grouped.shape
+    C = row - 4
+    dev = grad_grouped.device
+    gf = torch.zeros(B, N, C, dtype=torch.float32, device=dev) if (need_feat and C) else None
+    gx = torch.zeros(B, N, 3, dtype=torch.float32, device=dev) if need_xyz else None
+    gn = torch.zeros(B, M, 3, dtype=torch.float32, device=dev) if need_new_xyz else None
+    _call("o3d_ballquery_group_grad", grad_grouped.data_ptr(), idx.data_ptr(), B, int(N), M, C, S, float(radius),
+          int(bool(normalize_xyz)), gf.data_ptr() if gf is not None else None,
+          gx.data_ptr() if gx is not None else None, gn.data_ptr() if gn is not None else None, _stream())
+    return gf, gx, gn
+
+
+def three_nn_interpolate(unknown, known, known_feat_cl):
+    """unknown (B,n,3), known (B,m,3), known_feat_cl (B,m,c) -> out_cl (B,n,c), idx (B,n,3), weight (B,n,3)."""
+    _chk_f(unknown, "unknown"); _chk_f(known, "known"); _chk_f(known_feat_cl, "known_feat_cl")
+    B, n, _ = unknown.shape
+    m, c = known_feat_cl.shape[1], known_feat_cl.shape[2]
+    out = torch.empty(B, n, c, dtype=torch.float32, device=unknown.device)
+    idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
+    w = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
+    _call("o3d_three_nn_interpolate", unknown.data_ptr(), known.data_ptr(), known_feat_cl.data_ptr(), B, n, m, c,
+          out.data_ptr(), idx.data_ptr(), w.data_ptr(), _stream())
+    return out, idx, w
+
+
+def three_nn_interpolate_grad(grad_out_cl, idx, weight, m):
+    _chk_f(grad_out_cl, "grad_out_cl"); _chk_i(idx, "idx"); _chk_f(weight, "weight")
+    B, n, c = grad_out_cl.shape
+    g = torch.zeros(B, int(m), c, dtype=torch.float32, device=grad_out_cl.device)
+    _call("o3d_three_nn_interpolate_grad", grad_out_cl.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, n, int(m), c,
+          g.data_ptr(), _stream())
+    return g

@@ -1,0 +1,26 @@
+"""Process-wide execution switches (read by the modules; no global state inside the native library)."""
+import contextlib
+import os
+
+_FUSED = os.environ.get("O3D_FUSED", "1") != "0"
+
+
+def fused_enabled() -> bool:
+    return _FUSED
+
+
+def set_fused(flag: bool) -> None:
+    global _FUSED
+    _FUSED = bool(flag)
+
+
+@contextlib.contextmanager
+def composed_mode():
+    """Run modules as the reference's op-by-op composition over the nine `_ext` kernels (cross-check path)."""
+    global _FUSED
+    old = _FUSED
+    _FUSED = False
+    try:
+        yield
+    finally:
+        _FUSED = old

@@ -1,0 +1,189 @@
+"""Generate the golden fixtures in tests/golden/*.npz by running the REFERENCE's own Python
+(/root/reference: pointnet2/utils/*.py, models/backbone/pointnet.py, models/head/*.py, models/bat.py,
+models/p2b.py, models/base_model.py — unmodified, imported from where they lie) on CPU.
+
+The reference's native dependency `pointnet2_ops._ext` (absent, see oracle/pointnet2_ops_ref.c) is replaced by the
+C oracle through oracle/ext_stub.py; its absent host-side dependencies (pytorch_lightning, easydict, torchmetrics,
+nuscenes, shapely, pyquaternion, datasets/*) are replaced by inert stand-ins, and `Tensor.cuda()` is neutralised
+because the reference hard-codes it (pointnet2_modules.py:56, base_model.py:151).
+
+So these vectors pin the COMPOSITION (QueryAndGroup, SA / FP modules, backbone, xcorr, RPN, whole-model
+forward, losses, gradients) against the reference itself; the nine ops underneath remain "parity unpinned".
+
+Run only inside the authoring container:   python tests/golden/make_golden.py
+The GPU box never reads /root/reference; it only sees the committed .npz files.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import ext_stub  # noqa: E402
+from _params import det_state_dict  # noqa: E402
+from open3dsot_b200.compat.easydict import EasyDict  # noqa: E402
+from open3dsot_b200.compat import lightning as _pl_shim  # noqa: E402
+from open3dsot_b200.datasets.synthetic import synthetic_siamese_batch  # noqa: E402
+from open3dsot_b200.config import load_yaml  # noqa: E402
+
+
+def install_stubs():
+    ext_stub.install()
+    torch.Tensor.cuda = lambda self, *a, **k: self  # reference hard-codes .cuda()
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    mod("easydict", EasyDict=EasyDict)
+    pl = mod("pytorch_lightning", LightningModule=_pl_shim.LightningModule)
+    pl.utilities = mod("pytorch_lightning.utilities")
+    pl.utilities.distributed = mod("pytorch_lightning.utilities.distributed")
+
+    class _Metric(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    mod("torchmetrics", Metric=_Metric, Accuracy=_Metric)
+    nus = mod("nuscenes"); nus.utils = mod("nuscenes.utils")
+    nus.utils.geometry_utils = mod("nuscenes.utils.geometry_utils")
+    ds = mod("datasets"); ds.points_utils = mod("datasets.points_utils")
+    ut = mod("utils")
+    ut.metrics = mod("utils.metrics", TorchSuccess=_Metric, TorchPrecision=_Metric,
+                     estimateOverlap=None, estimateAccuracy=None)
+    sys.path.insert(0, REF)  # `pointnet2`, `models` resolve to the reference packages
+
+
+def np_(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def gen_modules(out):
+    from pointnet2.utils import pointnet2_utils as ru, pointnet2_modules as rm
+    from models.head.xcorr import P2B_XCorr, BoxAwareXCorr
+    from models.head.rpn import P2BVoteNetRPN
+    g = torch.Generator().manual_seed(11)
+    B, N, C, M = 2, 96, 8, 24
+    xyz = torch.rand(B, N, 3, generator=g) * 1.2
+    xyz[:, 10:20] = xyz[:, 0:10]                      # exact duplicates -> ties
+    feats = torch.randn(B, C, N, generator=g)
+    new_xyz = xyz[:, :M].contiguous()
+    out["qg_xyz"], out["qg_feats"] = np_(xyz), np_(feats)
+    for norm in (False, True):
+        qg = ru.QueryAndGroup(0.35, 16, use_xyz=True, return_idx=True, normalize_xyz=norm)
+        nf, idx = qg(xyz, new_xyz, feats)
+        out[f"qg_out_norm{int(norm)}"], out[f"qg_idx_norm{int(norm)}"] = np_(nf), np_(idx)
+
+    # SA module, train + eval, FPS and arange centres
+    for tag, use_fps in (("fps", True), ("arange", False)):
+        sa = rm.PointnetSAModule(mlp=[C, 16, 16, 32], radius=0.35, nsample=16, use_fps=use_fps)
+        sa.load_state_dict(det_state_dict(sa.state_dict(), seed=1))
+        x_in = xyz.clone().requires_grad_(False)
+        f_in = feats.clone().requires_grad_(True)
+        sa.train()
+        nx, nf, sidx = sa(x_in, f_in, M, True)
+        nf.square().sum().backward()
+        out[f"sa_{tag}_train_out"], out[f"sa_{tag}_idx"], out[f"sa_{tag}_newxyz"] = np_(nf), np_(sidx), np_(nx)
+        out[f"sa_{tag}_train_gfeat"] = np_(f_in.grad)
+        out[f"sa_{tag}_train_gw0"] = np_(sa.mlps[0].layer0.conv.weight.grad)
+        out[f"sa_{tag}_train_gw2"] = np_(sa.mlps[0].layer2.conv.weight.grad)
+        out[f"sa_{tag}_train_ggamma1"] = np_(sa.mlps[0].layer1.bn.bn.weight.grad)
+        out[f"sa_{tag}_rm2"] = np_(sa.mlps[0].layer2.bn.bn.running_mean)
+        out[f"sa_{tag}_rv2"] = np_(sa.mlps[0].layer2.bn.bn.running_var)
+        sa.eval()
+        sa.load_state_dict(det_state_dict(sa.state_dict(), seed=1))
+        _, nf_e, _ = sa(x_in, feats, M, True)
+        out[f"sa_{tag}_eval_out"] = np_(nf_e)
+
+    # FP module
+    fp = rm.PointnetFPModule(mlp=[C + 4, 16, 12])
+    fp.load_state_dict(det_state_dict(fp.state_dict(), seed=2))
+    fp.train()
+    unknown, known = xyz[:, :48].contiguous(), xyz[:, 40:72].contiguous()
+    uf = torch.randn(B, 4, 48, generator=g)
+    kf = torch.randn(B, C, 32, generator=g).requires_grad_(True)
+    y = fp(unknown, known, uf, kf)
+    y.square().sum().backward()
+    out["fp_unknown"], out["fp_known"], out["fp_uf"], out["fp_kf"] = np_(unknown), np_(known), np_(uf), np_(kf)
+    out["fp_out"], out["fp_gkf"] = np_(y), np_(kf.grad)
+
+    # xcorr heads + rpn (small channel counts)
+    f, hid, Mt, Ns = 16, 16, 12, 20
+    tf = torch.randn(B, f, Mt, generator=g); sf = torch.randn(B, f, Ns, generator=g)
+    txyz = torch.rand(B, Mt, 3, generator=g); sxyz = torch.rand(B, Ns, 3, generator=g)
+    tbc = torch.rand(B, Mt, 9, generator=g); sbc = torch.rand(B, Ns, 9, generator=g)
+    for k_, v_ in dict(xc_tf=tf, xc_sf=sf, xc_txyz=txyz, xc_sxyz=sxyz, xc_tbc=tbc, xc_sbc=sbc).items():
+        out[k_] = np_(v_)
+    px = P2B_XCorr(f, hid, f); px.load_state_dict(det_state_dict(px.state_dict(), seed=3)); px.train()
+    out["p2bx_out"] = np_(px(tf, sf, txyz))
+    bx = BoxAwareXCorr(f, hid, f, k=4, bc_channel=9); bx.load_state_dict(det_state_dict(bx.state_dict(), seed=4))
+    bx.train()
+    out["bax_out"] = np_(bx(tf, sf, txyz, sxyz, tbc, sbc))
+    rp = P2BVoteNetRPN(f, vote_channel=f, num_proposal=8); rp.load_state_dict(det_state_dict(rp.state_dict(), seed=5))
+    rp.train()
+    boxes, cla, vxyz, cen = rp(sxyz, sf)
+    out["rpn_boxes"], out["rpn_cla"], out["rpn_vote_xyz"], out["rpn_centers"] = np_(boxes), np_(cla), np_(vxyz), np_(cen)
+
+
+def gen_model(name, cfg_file, B, M, N, out, seed):
+    from models import get_model
+    cfg = EasyDict(load_yaml(os.path.join(ROOT, "cfgs", cfg_file)))
+    net = get_model(cfg.net_model)(cfg)
+    net.load_state_dict(det_state_dict(net.state_dict(), seed=seed), strict=False)
+    net.train()
+    net.log = lambda *a, **k: None
+    batch = synthetic_siamese_batch(B, M, N, seed=1234 + seed, box_aware=(name == "bat"))
+    b2 = {k: v.clone() for k, v in batch.items()}
+    loss = net.training_step(b2, 0)
+    loss.backward()
+    out[f"{name}_loss"] = np_(loss)
+    sd = dict(net.named_parameters())
+    for k in ("conv_final.bias", "backbone.SA_modules.0.mlps.0.layer0.conv.weight",
+              "backbone.SA_modules.2.mlps.0.layer2.bn.bn.weight", "rpn.vote_layer.2.conv.bias",
+              "xcorr.mlp.layer0.conv.weight", "rpn.FC_proposal.2.conv.weight"):
+        out[f"{name}_grad::{k}"] = np_(sd[k].grad)[:16]   # first rows only: keeps the fixture small
+    out[f"{name}_gradnorms"] = np.array([float(p.grad.norm()) for _, p in sorted(sd.items())], dtype=np.float64)
+    # forward outputs in train mode (fresh copy so that running stats restart from the same state)
+    net.load_state_dict(det_state_dict(net.state_dict(), seed=seed), strict=False)
+    with torch.no_grad():
+        ep = net(batch)
+    for k in ("estimation_boxes", "estimation_cla", "vote_xyz", "center_xyz", "sample_idxs"):
+        out[f"{name}_{k}"] = np_(ep[k])
+    if "pred_search_bc" in ep:
+        out[f"{name}_pred_search_bc"] = np_(ep["pred_search_bc"])
+    net.eval()
+    net.load_state_dict(det_state_dict(net.state_dict(), seed=seed), strict=False)
+    with torch.no_grad():
+        ep = net(batch)
+    out[f"{name}_eval_boxes"] = np_(ep["estimation_boxes"])
+    out[f"{name}_eval_cla"] = np_(ep["estimation_cla"])
+
+
+def main():
+    assert os.path.isdir(REF), "golden vectors can only be generated where /root/reference exists"
+    install_stubs()
+    torch.set_num_threads(8)
+    mods = {}
+    gen_modules(mods)
+    np.savez_compressed(os.path.join(HERE, "ref_modules.npz"), **mods)
+    models = {}
+    gen_model("bat", "BAT_Car.yaml", 2, 256, 512, models, seed=21)
+    gen_model("p2b", "P2B_Car.yaml", 1, 256, 512, models, seed=22)   # BASELINE.json configs[0]
+    np.savez_compressed(os.path.join(HERE, "ref_models.npz"), **models)
+    for f in ("ref_modules.npz", "ref_models.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

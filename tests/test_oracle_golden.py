@@ -1,0 +1,138 @@
+"""The oracle's functional restatement (oracle/modules.py) against the golden vectors produced by the
+REFERENCE's own Python (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _params import det_state_dict
+from oracle import modules as om
+from open3dsot_b200.config import load_config
+from open3dsot_b200.datasets.synthetic import synthetic_siamese_batch
+from open3dsot_b200.models import get_model
+from open3dsot_b200.pointnet2.utils import pointnet2_modules as pm
+from open3dsot_b200.models.head.xcorr import P2B_XCorr, BoxAwareXCorr
+from open3dsot_b200.models.head.rpn import P2BVoteNetRPN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-4  # north_star: float features within 1e-4 relative
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double()
+    b = torch.as_tensor(b).detach().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def gm(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "ref_modules.npz")))
+
+
+@pytest.fixture(scope="module")
+def gmod(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "ref_models.npz")))
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def test_query_and_group(gm):
+    xyz, feats = _t(gm["qg_xyz"]), _t(gm["qg_feats"])
+    new_xyz = xyz[:, :24].contiguous()
+    for norm in (0, 1):
+        g, idx = om.query_and_group(xyz, new_xyz, feats, 0.35, 16, True, bool(norm))
+        assert np.array_equal(idx.numpy(), gm[f"qg_idx_norm{norm}"])
+        assert rel(g, gm[f"qg_out_norm{norm}"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag,use_fps", [("fps", True), ("arange", False)])
+def test_sa_module_train_eval_and_grads(gm, tag, use_fps):
+    xyz, feats = _t(gm["qg_xyz"]), _t(gm["qg_feats"])
+    sa = pm.PointnetSAModule(mlp=[8, 16, 16, 32], radius=0.35, nsample=16, use_fps=use_fps)
+    sd = {"sa." + k: v.clone() for k, v in det_state_dict(sa.state_dict(), seed=1).items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    f_in = feats.clone().requires_grad_(True)
+    nx, nf, sidx = om.sa_module(sd, "sa", xyz, f_in, 24, 0.35, 16, use_fps, True)
+    assert np.array_equal(sidx.numpy(), gm[f"sa_{tag}_idx"])
+    assert rel(nx, gm[f"sa_{tag}_newxyz"]) == 0
+    assert rel(nf, gm[f"sa_{tag}_train_out"]) < RTOL
+    nf.square().sum().backward()
+    assert rel(f_in.grad, gm[f"sa_{tag}_train_gfeat"]) < RTOL
+    assert rel(sd["sa.mlps.0.layer0.conv.weight"].grad, gm[f"sa_{tag}_train_gw0"]) < RTOL
+    assert rel(sd["sa.mlps.0.layer2.conv.weight"].grad, gm[f"sa_{tag}_train_gw2"]) < RTOL
+    assert rel(sd["sa.mlps.0.layer1.bn.bn.weight"].grad, gm[f"sa_{tag}_train_ggamma1"]) < RTOL
+    assert rel(sd["sa.mlps.0.layer2.bn.bn.running_mean"], gm[f"sa_{tag}_rm2"]) < 1e-5
+    assert rel(sd["sa.mlps.0.layer2.bn.bn.running_var"], gm[f"sa_{tag}_rv2"]) < 1e-5
+    sd2 = {"sa." + k: v.clone() for k, v in det_state_dict(sa.state_dict(), seed=1).items()}
+    _, nf_e, _ = om.sa_module(sd2, "sa", xyz, feats, 24, 0.35, 16, use_fps, False)
+    assert rel(nf_e, gm[f"sa_{tag}_eval_out"]) < RTOL
+
+
+def test_fp_module(gm):
+    fp = pm.PointnetFPModule(mlp=[12, 16, 12])
+    sd = {"fp." + k: v.clone() for k, v in det_state_dict(fp.state_dict(), seed=2).items()}
+    kf = _t(gm["fp_kf"]).requires_grad_(True)
+    y = om.fp_module(sd, "fp", _t(gm["fp_unknown"]), _t(gm["fp_known"]), _t(gm["fp_uf"]), kf, True)
+    assert rel(y, gm["fp_out"]) < RTOL
+    y.square().sum().backward()
+    assert rel(kf.grad, gm["fp_gkf"]) < RTOL
+
+
+def test_xcorr_and_rpn(gm):
+    tf, sf, txyz, sxyz, tbc, sbc = (_t(gm[k]) for k in ("xc_tf", "xc_sf", "xc_txyz", "xc_sxyz", "xc_tbc", "xc_sbc"))
+    px = P2B_XCorr(16, 16, 16)
+    sd = {"x." + k: v for k, v in det_state_dict(px.state_dict(), seed=3).items()}
+    assert rel(om.p2b_xcorr(sd, "x", tf, sf, txyz, True), gm["p2bx_out"]) < RTOL
+    bx = BoxAwareXCorr(16, 16, 16, k=4, bc_channel=9)
+    sd = {"x." + k: v for k, v in det_state_dict(bx.state_dict(), seed=4).items()}
+    out, _ = om.boxaware_xcorr(sd, "x", tf, sf, txyz, sxyz, tbc, sbc, 4, True)
+    assert rel(out, gm["bax_out"]) < RTOL
+    rp = P2BVoteNetRPN(16, vote_channel=16, num_proposal=8)
+    sd = {"r." + k: v for k, v in det_state_dict(rp.state_dict(), seed=5).items()}
+    boxes, cla, vxyz, cen = om.rpn(sd, "r", sxyz, sf, 8, True)
+    assert rel(boxes, gm["rpn_boxes"]) < RTOL and rel(cla, gm["rpn_cla"]) < RTOL
+    assert rel(vxyz, gm["rpn_vote_xyz"]) < RTOL and rel(cen, gm["rpn_centers"]) < RTOL
+
+
+@pytest.mark.parametrize("name,cfg_file,B,seed", [("bat", "BAT_Car.yaml", 2, 21), ("p2b", "P2B_Car.yaml", 1, 22)])
+def test_whole_model_forward_loss_grads(gmod, name, cfg_file, B, seed):
+    cfg = load_config(os.path.join(ROOT, "cfgs", cfg_file))
+    net = get_model(cfg.net_model)(cfg)           # only used for the state-dict key/shape surface
+    base = det_state_dict(net.state_dict(), seed=seed)
+    batch = synthetic_siamese_batch(B, 256, 512, seed=1234 + seed, box_aware=(name == "bat"))
+    fwd = om.bat_forward if name == "bat" else om.p2b_forward
+    trn = om.bat_training_loss if name == "bat" else om.p2b_training_loss
+
+    sd = {k: v.clone() for k, v in base.items()}
+    with torch.no_grad():
+        ep = fwd(sd, cfg, batch, True)
+    assert np.array_equal(ep["sample_idxs"].numpy(), gmod[f"{name}_sample_idxs"])
+    for k in ("estimation_boxes", "estimation_cla", "vote_xyz", "center_xyz"):
+        assert rel(ep[k], gmod[f"{name}_{k}"]) < RTOL, k
+    if name == "bat":
+        assert rel(ep["pred_search_bc"], gmod["bat_pred_search_bc"]) < RTOL
+
+    sd = {k: v.clone() for k, v in base.items()}
+    with torch.no_grad():
+        ep = fwd(sd, cfg, batch, False)
+    assert rel(ep["estimation_boxes"], gmod[f"{name}_eval_boxes"]) < RTOL
+    assert rel(ep["estimation_cla"], gmod[f"{name}_eval_cla"]) < RTOL
+
+    sd = {k: v.clone() for k, v in base.items()}
+    pnames = [k for k, _ in net.named_parameters()]
+    for k in pnames:
+        sd[k].requires_grad_(True)
+    loss, _, _ = trn(sd, cfg, {k: v.clone() for k, v in batch.items()})
+    assert rel(loss, gmod[f"{name}_loss"]) < RTOL
+    loss.backward()
+    for key in gmod:
+        if key.startswith(f"{name}_grad::"):
+            p = key.split("::")[1]
+            assert rel(sd[p].grad[:16], gmod[key]) < 5e-4, p
+    norms = np.array([float(sd[k].grad.norm()) for k in sorted(pnames)])
+    assert np.allclose(norms, gmod[f"{name}_gradnorms"], rtol=2e-3, atol=1e-7)
