@@ -1,0 +1,298 @@
+"""bench.py — BAT-Car forward+backward(+Adam) template–search pairs/s on synthetic KITTI-Car-shaped pairs.
+
+Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W`; for N>1 the driver launches it under
+torchrun, one rank per GPU.  Rank 0 prints ONE JSON line.
+
+  value        whole-job pairs/s with the batch already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e          the same metric through the public API `model.training_step(batch)` fed from PINNED HOST memory:
+               H2D copy of the batch + the step + D2H read of the loss inside the timed region
+  roofline     the dominant kernel timed alone, live, with CUDA events on its launch stream
+  cpu_baseline the oracle (CPU restatement of the reference path) on a bounded sample of the same workload
+  --impl reference   times only that CPU path (the reference ships no CPU/native code of its own: SURVEY.md facts 1-3)
+
+A "step" = one optimisation step of BAT_Car.yaml at batch 48 per GPU (BASELINE.json configs[1]); weak scaling.
+Timing hygiene: >= 3 warm-up steps, L2 flushed (256 MiB write) between timed steps and excluded from the timing,
+clocks sampled with nvidia-smi during the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG_FILE = os.path.join(ROOT, "cfgs", "BAT_Car.yaml")
+WORKLOAD = "BAT_Car.yaml train step (fwd+bwd+Adam), synthetic KITTI-Car pairs, template 512 / search 1024 pts, batch 48/GPU"
+METRIC = "template-search pairs/sec, BAT-Car fwd+bwd"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=48, help="pairs per GPU (BAT_Car.yaml config 2: 48)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=4, help="pairs per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused", type=int, default=None, help="override O3D_FUSED (1 = fused kernels, 0 = composed)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower() == "active"})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(batch_pairs, steps, seed=20260924):
+    """The oracle's BAT training step (forward + backward; no optimizer) on the host cores."""
+    from open3dsot_b200.config import load_config
+    from open3dsot_b200.datasets.synthetic import synthetic_siamese_batch
+    from open3dsot_b200.models import get_model
+    from oracle import modules as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = load_config(CFG_FILE)
+    torch.manual_seed(0)
+    net = get_model(cfg.net_model)(cfg)
+    pnames = [k for k, _ in net.named_parameters()]
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    for k in pnames:
+        sd[k].requires_grad_(True)
+    batch = synthetic_siamese_batch(batch_pairs, cfg.template_size, cfg.search_size, seed=seed)
+    times = []
+    for i in range(steps + 1):
+        for k in pnames:
+            sd[k].grad = None
+        t0 = time.perf_counter()
+        loss, _, _ = om.bat_training_loss(sd, cfg, {k: v.clone() for k, v in batch.items()})
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i > 0:  # first iteration = warm-up
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": batch_pairs / med, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"oracle BAT fwd+bwd, batch {batch_pairs} pairs of 512/1024 pts, median of {steps} steps after 1 warm-up",
+            "ms_per_step": med * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args.cpu_batch, max(1, min(args.steps, 5)))
+    line = {"metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "note": "CPU path = oracle port (the reference has no CPU/native code)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def roofline_probe(dev, batch_pairs):
+    """Time the dominant bandwidth-bound kernel alone (CUDA events on the launch stream, L2 flushed by size:
+    output >> 126 MB).  Kernel: fused ball query + grouping of the SA3 search layer shape (the largest grouped
+    tensor of the model): xyz (B,256,3), features (B,256,256) -> grouped (B,128,32,260)."""
+    from open3dsot_b200 import ops
+    from open3dsot_b200.datasets.synthetic import synthetic_siamese_batch
+    B = max(batch_pairs, 48) * 4           # 192 clouds -> 816 MB written per launch (> L2)
+    b = synthetic_siamese_batch(min(B, 64), 512, 1024, seed=1)
+    xyz = b["search_points"][:, :256].contiguous().to(dev)
+    reps = (B + xyz.shape[0] - 1) // xyz.shape[0]
+    xyz = xyz.repeat(reps, 1, 1)[:B].contiguous()
+    feat = torch.randn(B, 256, 256, device=dev)
+    new_xyz = xyz[:, :128].contiguous()
+    for _ in range(3):
+        grouped, idx = ops.ballquery_group(xyz, new_xyz, feat, 0.7, 32, False)
+    torch.cuda.synchronize()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        grouped, idx = ops.ballquery_group(xyz, new_xyz, feat, 0.7, 32, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    alg_bytes = grouped.numel() * 4 + idx.numel() * 4 + xyz.numel() * 4 + new_xyz.numel() * 4 + feat.numel() * 4
+    peaks, how = measured_peaks()
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    return {"kernel": "ballquery_group_kernel (SA3-search shape, B=%d)" % B, "bound": "hbm", "achieved": ach,
+            "peak": peaks["hbm_gbs"], "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
+            "algorithmic_bytes_per_launch": alg_bytes}
+
+
+def run_ours(args):
+    from open3dsot_b200 import ddp, ops, runtime
+    from open3dsot_b200.config import load_config
+    from open3dsot_b200.datasets.synthetic import synthetic_siamese_batch
+    from open3dsot_b200.models import get_model
+    import torch.distributed as dist
+
+    if args.fused is not None:
+        runtime.set_fused(bool(args.fused))
+    rank, world, local = ddp.init_distributed()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    cfg = load_config(CFG_FILE, {"batch_size": args.batch})
+    torch.manual_seed(0)
+    net = get_model(cfg.net_model)(cfg).to(dev).train()
+    flat = ddp.FlatParams(net)
+    ddp.broadcast_parameters(flat, net)
+    opt = torch.optim.Adam([flat.flat], lr=cfg.lr, betas=(0.5, 0.999), eps=1e-6, weight_decay=cfg.wd, fused=True)
+    flat.flat.grad = flat.grad
+
+    # distinct host batches (pinned), one device-resident copy of each
+    n_batches = 4
+    host = [synthetic_siamese_batch(args.batch, cfg.template_size, cfg.search_size, seed=20260924 + rank * 100 + i,
+                                    pin_memory=True) for i in range(n_batches)]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step(batch):
+        flat.zero_grad()
+        loss = net.training_step(batch, 0)
+        loss.backward()
+        ddp.allreduce_gradients(flat)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step({k: v.clone() for k, v in resident[i % n_batches].items()})
+    barrier()
+
+    # ---- device-resident timing
+    ops.LAUNCHES = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(float(i))                                   # evict L2; not timed
+        batch = {k: v.clone() for k, v in resident[i % n_batches].items()}
+        evs[i][0].record()
+        step(batch)
+        evs[i][1].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = ops.LAUNCHES
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+
+    # ---- end-to-end timing: pinned host batch -> H2D -> step -> loss D2H, every step
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    last = 0.0
+    for i in range(args.steps):
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
+        last = float(step(batch).item())                       # D2H read of the loss (4 bytes) + host sync
+    e1.record()
+    barrier()
+    e2e_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    roof = roofline_probe(dev, args.batch)
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(args.cpu_batch, args.cpu_steps)
+    pairs = args.batch * world * args.steps
+    line = {"metric": METRIC, "value": pairs / (dev_ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                       "mode": "fused" if runtime.fused_enabled() else "composed",
+                       "l2": "256 MiB flush write between timed steps, excluded from timing",
+                       "optimizer": "Adam(0.5,0.999) on the flat parameter bucket", "last_loss": last},
+            "clocks": clocks, "gpu_launches": launches, "wall_s_timed_region": wall,
+            "e2e": {"value": pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / args.steps * 1e3},
+            "roofline": roof, "cpu_baseline": cb}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

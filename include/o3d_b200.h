@@ -109,6 +109,63 @@ int o3d_three_nn_interpolate(const float* unknown, const float* known, const flo
 int o3d_three_nn_interpolate_grad(const float* grad_out_cl, const int32_t* idx, const float* weight, int B, int n, int m,
                                   int c, float* grad_known_feat_cl, void* stream);
 
+/* BoxAwareXCorr grouping by an explicit (top-k) index list (models/head/xcorr.py:87-90), channels-last:
+ * feat_cl (B,N,C), idx (B,L) -> out_cl (B,L,C); the gradient is accumulated into a pre-zeroed (B,N,C).   */
+int o3d_group_rows(const float* feat_cl, const int32_t* idx, int B, int N, int L, int C, float* out_cl, void* stream);
+int o3d_group_rows_grad(const float* grad_out_cl, const int32_t* idx, int B, int N, int L, int C, float* grad_feat_cl,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block 3 — point-wise MLP layers (SharedMLP / Seq of the reference: 1x1 conv + BatchNorm + ReLU
+ * [+ max-pool over nsample / k / template points]; pointnet2/utils/pytorch_utils.py:12-37,68-121,
+ * pointnet2_modules.py:64-73, models/head/xcorr.py:47-51,98-101).
+ * Activations are channels-last matrices X[P, ld] (ld % 4 == 0, 16-byte aligned rows); weights are
+ * zero-padded to multiples of 4 in both dimensions.  All statistics buffers are fp64, pre-zeroed.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Y[p,n] = sum_k A(X)[p,k] * wt[k,n] (+ bias[n]),  A(v) = relu?(v*in_scale[k] + in_shift[k]) (scale/shift nullable).
+ * wt is the TRANSPOSED weight [K, ldw].  Optional outputs: y (raw pre-BN, nullable), sum / sumsq (per-channel
+ * batch statistics), and for S > 0 the per-group (S consecutive positions; S | 128, S | P) ymax / ymin / arg
+ * (argmax | argmin << 16), each [P/S, ldp].                                                        */
+int o3d_pw_fwd(const float* x, int ldx, const float* in_scale, const float* in_shift, int in_relu, const float* wt,
+               int ldw, const float* bias, int P, int K, int N, float* y, int ldy, double* sum, double* sumsq, int S,
+               float* ymax, float* ymin, int32_t* arg, int ldp, void* stream);
+
+/* The layer's output gradient is given implicitly as  dY = a*g + b + cc*y  (batch-norm backward; a == NULL -> dY = g)
+ * with g either dense [P, ldg] or pooled: g[p,c] = (p % S == sel[p/S,c]) ? dpool[p/S,c] : 0.
+ * dgrad: out[p,n] = sum_c dY[p,c] * w[c,n]; if yprev != NULL the previous layer's ReLU mask
+ *        [yprev*pscale+pshift > 0] is applied and s1 += out, s2y += out*yprev are accumulated.      */
+int o3d_pw_dgrad(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
+                 const float* dpool, const int32_t* sel, int S, int ldp, const float* w, int ldw, int P, int Cout,
+                 int Cin, float* out, int ldo, const float* yprev, int ldyp, const float* pscale, const float* pshift,
+                 int prelu, double* s1, double* s2y, void* stream);
+
+/* wgrad: dw[m,n] += sum_p dY[p,m] * A(X)[p,n]   (dw pre-zeroed, [Cout, lddw], fp32 reductions)       */
+int o3d_pw_wgrad(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
+                 const float* dpool, const int32_t* sel, int S, int ldp, const float* x, int ldx, const float* in_scale,
+                 const float* in_shift, int in_relu, int P, int Cout, int Cin, float* dw, int lddw, void* stream);
+
+/* BatchNorm bookkeeping (torch semantics: biased variance to normalise, unbiased for running_var, momentum
+ * update, num_batches_tracked += 1): scale = gamma*invstd, shift = beta - mean*scale.               */
+int o3d_bn_fwd_finalize(const double* sum, const double* sumsq, double count, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                        float eps, int training, int C, float* scale, float* shift, float* mean, float* invstd,
+                        void* stream);
+int o3d_bn_bwd_finalize(const double* s1, const double* s2y, double count, const float* gamma, const float* mean,
+                        const float* invstd, int training, int C, float* a, float* b, float* cc, float* dgamma,
+                        float* dbeta, void* stream);
+
+/* Pooled activation: out[g,c] = relu?(scale*ysel + shift), ysel = scale >= 0 ? ymax : ymin, sel = its position. */
+int o3d_pool_finalize(const float* ymax, const float* ymin, const int32_t* arg, const float* scale, const float* shift,
+                      int relu, int G, int C, int ldp, float* out, int ldo, int32_t* sel, float* ysel, void* stream);
+int o3d_pool_bwd_prep(const float* dout, int ldd, const float* out, int ldo, const float* ysel, int relu, int G, int C,
+                      int ldp, float* dpool, double* s1, double* s2y, void* stream);
+/* Dense activation and its backward preparation (g = dout * [out > 0], s1 = sum g, s2y = sum g*y).   */
+int o3d_act_apply(const float* y, int ldy, const float* scale, const float* shift, int relu, int P, int C, float* out,
+                  int ldo, void* stream);
+int o3d_dense_bwd_prep(const float* dout, int ldd, const float* out, int ldo, const float* y, int ldy, int relu, int P,
+                       int C, float* g, int ldg, double* s1, double* s2y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

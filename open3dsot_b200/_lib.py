@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libo3d_b200.so")
 _p = ctypes.c_void_p
 _i = ctypes.c_int
 _f = ctypes.c_float
+_d = ctypes.c_double
 
 # name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/o3d_b200.h
 PROTOTYPES = {
@@ -32,6 +33,18 @@ PROTOTYPES = {
     "o3d_ballquery_group_grad": [_p, _p, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p],
     "o3d_three_nn_interpolate": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
     "o3d_three_nn_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "o3d_group_rows": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "o3d_group_rows_grad": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "o3d_pw_fwd": [_p, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p],
+    "o3d_pw_dgrad": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _p, _p,
+                     _p],
+    "o3d_pw_wgrad": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p],
+    "o3d_bn_fwd_finalize": [_p, _p, _d, _p, _p, _p, _p, _p, _f, _f, _i, _i, _p, _p, _p, _p, _p],
+    "o3d_bn_bwd_finalize": [_p, _p, _d, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p],
+    "o3d_pool_finalize": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p],
+    "o3d_pool_bwd_prep": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "o3d_act_apply": [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p],
+    "o3d_dense_bwd_prep": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p],
 }
 _RESTYPE = {"o3d_last_error": ctypes.c_char_p}
 

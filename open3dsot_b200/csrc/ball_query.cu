@@ -167,6 +167,35 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Channels-last row gather by an explicit index list (BoxAware top-k grouping, xcorr.py:87-90):
+//   out[b, j, s, :] = feat[b, idx[b,j,s], :]      one warp per output row, float4 per lane.
+__global__ void __launch_bounds__(256)
+    group_rows_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx, int N, int L, int C,
+                      float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = C >> 2;
+    for (int r = blockIdx.x * 8 + warp; r < L; r += gridDim.x * 8) {
+        const int k = idx[(size_t)b * L + r];
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(feat + ((size_t)b * N + k) * C);
+        float4* __restrict__ dst = reinterpret_cast<float4*>(out + ((size_t)b * L + r) * C);
+        for (int v = lane; v < c4; v += 32) dst[v] = __ldg(src + v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    group_rows_grad_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx, int N, int L, int C,
+                           float* __restrict__ gfeat) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = blockIdx.x * 8 + warp; r < L; r += gridDim.x * 8) {
+        const int k = idx[(size_t)b * L + r];
+        const float* __restrict__ g = gout + ((size_t)b * L + r) * C;
+        float* __restrict__ dst = gfeat + ((size_t)b * N + k) * C;
+        for (int v = lane * 4; v < C; v += 128) atomicAdd(reinterpret_cast<float4*>(dst + v), *reinterpret_cast<const float4*>(g + v));
+    }
+}
+
 }  // namespace
 
 extern "C" int o3d_ball_query(const float* new_xyz, const float* xyz, int B, int N, int M, float radius, int nsample,
@@ -225,5 +254,33 @@ extern "C" int o3d_ballquery_group_grad(const float* grad_grouped_cl, const int3
                                                                          normalize_xyz ? 1.0f / radius : 1.0f,
                                                                          grad_feat_cl, grad_xyz, grad_new_xyz);
     O3D_CHECK_LAUNCH("o3d_ballquery_group_grad");
+    return O3D_OK;
+}
+
+extern "C" int o3d_group_rows(const float* feat_cl, const int32_t* idx, int B, int N, int L, int C, float* out_cl,
+                              void* stream) {
+    O3D_REQUIRE(feat_cl && idx && out_cl, O3D_ERR_ARG, "o3d_group_rows: null pointer");
+    O3D_REQUIRE((C & 3) == 0, O3D_ERR_ARG, "o3d_group_rows: C must be a multiple of 4");
+    O3D_REQUIRE(((uintptr_t)feat_cl & 15) == 0 && ((uintptr_t)out_cl & 15) == 0, O3D_ERR_ALIGN,
+                "o3d_group_rows: pointers must be 16-byte aligned");
+    if (B == 0 || L == 0 || C == 0) return O3D_OK;
+    int gx = (L + 7) / 8;
+    const int cap = o3d_num_sms() * 8;
+    if (gx > cap) gx = cap;
+    group_rows_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(feat_cl, idx, N, L, C, out_cl);
+    O3D_CHECK_LAUNCH("o3d_group_rows");
+    return O3D_OK;
+}
+
+extern "C" int o3d_group_rows_grad(const float* grad_out_cl, const int32_t* idx, int B, int N, int L, int C,
+                                   float* grad_feat_cl, void* stream) {
+    O3D_REQUIRE(grad_out_cl && idx && grad_feat_cl, O3D_ERR_ARG, "o3d_group_rows_grad: null pointer");
+    O3D_REQUIRE((C & 3) == 0, O3D_ERR_ARG, "o3d_group_rows_grad: C must be a multiple of 4");
+    if (B == 0 || L == 0 || C == 0) return O3D_OK;
+    int gx = (L + 7) / 8;
+    const int cap = o3d_num_sms() * 8;
+    if (gx > cap) gx = cap;
+    group_rows_grad_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(grad_out_cl, idx, N, L, C, grad_feat_cl);
+    O3D_CHECK_LAUNCH("o3d_group_rows_grad");
     return O3D_OK;
 }

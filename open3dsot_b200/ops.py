@@ -30,7 +30,12 @@ def _chk_i(t, name):
         raise RuntimeError(f"{name} must be a contiguous tensor")
 
 
+LAUNCHES = 0  # kernels enqueued through the C ABI (bench.py reports it as gpu_launches)
+
+
 def _call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
     _lib.check(getattr(_lib.lib(), name)(*args), name)
 
 

@@ -20,6 +20,9 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        # the composed cross-check path runs torch convs: keep them in true fp32 so 1e-4 parity is meaningful
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
