@@ -166,6 +166,62 @@ int o3d_act_apply(const float* y, int ldy, const float* scale, const float* shif
 int o3d_dense_bwd_prep(const float* dout, int ldd, const float* out, int ldo, const float* y, int ldy, int relu, int P,
                        int C, float* g, int ldg, double* s1, double* s2y, void* stream);
 
+/* Tensor-core (tcgen05 / TMEM, 3xTF32) variants of o3d_pw_fwd / o3d_pw_dgrad for >= 128 output channels and
+ * K >= 32.  The weight operand is passed pre-tiled: o3d_pw_tc_pretile() rewrites a row-major matrix
+ * w[rows, ldw] (rows = the GEMM's output channels, K contiguous) into per-(128-row tile, 32-wide k-block)
+ * shared-memory images [hi | lo], K-major SWIZZLE_128B, that the kernel streams with cp.async.bulk.
+ * forward:  rows = Cout, K = Cin   (w = the padded conv weight)
+ * dgrad  :  rows = Cin,  K = Cout  (w = its transpose)                                                */
+long long o3d_pw_tc_wtile_bytes(int rows, int K);
+int o3d_pw_tc_pretile(const float* w, int ldw, int rows, int K, void* wtiles, void* stream);
+int o3d_pw_fwd_tc(const float* x, int ldx, const float* in_scale, const float* in_shift, int in_relu, const void* wtiles,
+                  const float* bias, int P, int K, int N, float* y, int ldy, double* sum, double* sumsq, int S,
+                  float* ymax, float* ymin, int32_t* arg, int ldp, void* stream);
+int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
+                    const float* dpool, const int32_t* sel, int S, int ldp, const void* wtiles_t, int P, int Cout,
+                    int Cin, float* out, int ldo, const float* yprev, int ldyp, const float* pscale,
+                    const float* pshift, int prelu, double* s1, double* s2y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block 4 — a whole MLP stack (SharedMLP / Seq) per call.  The descriptor carries the raw parameter
+ * pointers of the reference modules in their checkpoint layout (weight [cout, cin] row-major, BN
+ * gamma/beta/running stats); packing, per-layer GEMMs, BN bookkeeping, pooling and — backward —
+ * BN-backward, wgrad, dgrad and un-packing of the gradients are all enqueued by one call.
+ * ---------------------------------------------------------------------------------------------- */
+#define O3D_MAX_LAYERS 8
+typedef struct o3d_stack_t {
+    int n_layers;   /* 1..O3D_MAX_LAYERS */
+    int P;          /* positions (rows of the channels-last input)                               */
+    int K0;         /* input row length (multiple of 4, zero padded)                             */
+    int S;          /* pooling group size over consecutive positions (0 = dense output)          */
+    int training;   /* BatchNorm uses batch statistics and updates the running ones              */
+    int use_tc;     /* allow the tcgen05 3xTF32 kernels where the shape qualifies                */
+    int xyz_first;  /* layer-0 weight columns are [xyz(3) | features(c0)], input rows [features | dx dy dz 0] */
+    int c0;         /* real feature channels of layer 0 when xyz_first                           */
+    int cin[O3D_MAX_LAYERS], cout[O3D_MAX_LAYERS], relu[O3D_MAX_LAYERS], has_bn[O3D_MAX_LAYERS];
+    float momentum[O3D_MAX_LAYERS], eps[O3D_MAX_LAYERS];
+    const float* weight[O3D_MAX_LAYERS];
+    const float* bias[O3D_MAX_LAYERS];
+    const float* gamma[O3D_MAX_LAYERS];
+    const float* beta[O3D_MAX_LAYERS];
+    float* running_mean[O3D_MAX_LAYERS];
+    float* running_var[O3D_MAX_LAYERS];
+    long long* num_batches_tracked[O3D_MAX_LAYERS];
+    /* backward outputs, same layouts as the parameters (NULL = not wanted) */
+    float* d_weight[O3D_MAX_LAYERS];
+    float* d_bias[O3D_MAX_LAYERS];
+    float* d_gamma[O3D_MAX_LAYERS];
+    float* d_beta[O3D_MAX_LAYERS];
+} o3d_stack_t;
+
+long long o3d_stack_workspace_bytes(const o3d_stack_t* d, int backward);
+/* out: [P or P/S, round4(cout_last)]; ws_fwd must stay alive (untouched) until the backward call. */
+int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float* out, int keep_for_backward,
+                      void* stream);
+/* dout: contiguous [rows, round4(cout_last)]; dx: [P, K0] or NULL. */
+int o3d_stack_backward(const o3d_stack_t* d, const float* x, const void* ws_fwd, void* ws_bwd, const float* out,
+                       const float* dout, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,8 +45,31 @@ PROTOTYPES = {
     "o3d_pool_bwd_prep": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p],
     "o3d_act_apply": [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p],
     "o3d_dense_bwd_prep": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p],
+    "o3d_pw_tc_wtile_bytes": [_i, _i],
+    "o3d_pw_tc_pretile": [_p, _i, _i, _i, _p, _p],
+    "o3d_pw_fwd_tc": [_p, _i, _p, _p, _i, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p],
+    "o3d_pw_dgrad_tc": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _p, _p,
+                        _p],
+    "o3d_stack_workspace_bytes": [_p, _i],
+    "o3d_stack_forward": [_p, _p, _p, _p, _i, _p],
+    "o3d_stack_backward": [_p, _p, _p, _p, _p, _p, _p, _p],
 }
-_RESTYPE = {"o3d_last_error": ctypes.c_char_p}
+_RESTYPE = {"o3d_last_error": ctypes.c_char_p, "o3d_pw_tc_wtile_bytes": ctypes.c_longlong,
+            "o3d_stack_workspace_bytes": ctypes.c_longlong}
+
+MAX_LAYERS = 8
+_I8, _F8, _P8 = ctypes.c_int * MAX_LAYERS, ctypes.c_float * MAX_LAYERS, ctypes.c_void_p * MAX_LAYERS
+
+
+class StackDesc(ctypes.Structure):
+    """ctypes mirror of `o3d_stack_t` (include/o3d_b200.h, block 4)."""
+    _fields_ = [("n_layers", _i), ("P", _i), ("K0", _i), ("S", _i), ("training", _i), ("use_tc", _i),
+                ("xyz_first", _i), ("c0", _i),
+                ("cin", _I8), ("cout", _I8), ("relu", _I8), ("has_bn", _I8),
+                ("momentum", _F8), ("eps", _F8),
+                ("weight", _P8), ("bias", _P8), ("gamma", _P8), ("beta", _P8),
+                ("running_mean", _P8), ("running_var", _P8), ("num_batches_tracked", _P8),
+                ("d_weight", _P8), ("d_bias", _P8), ("d_gamma", _P8), ("d_beta", _P8)]
 
 _lib = None
 

@@ -91,7 +91,7 @@ __device__ __forceinline__ float4 load_dy(const DyIn& in, int p, int P, int c, i
 
 // ------------------------------------------------------------------------------------------------------------
 // Shared-memory plan (dynamic):  main loop  As[2][BM*AS_LD] | Bs[2][BK*(BN+4)]   (or A2s[2][BK*(BM+4)] for wgrad)
-//                                epilogue   Cs[BM][BN+4]  (aliases the main-loop buffers)  + red[8][BN][2]
+//                                epilogue   Cs[BM][BN+4]  (aliases the main-loop buffers)  + red[NT/(BN/4)][BN][2]
 template <int BN>
 struct Cfg {
     static constexpr int TX = BN / 8;         // threads along N (each owns 4 + 4 columns)
@@ -102,7 +102,7 @@ struct Cfg {
     static constexpr int A2_LD = BM + 4;
     static constexpr size_t MAIN_FLOATS = 2 * BM * AS_LD + 2 * BK * BS_LD;
     static constexpr size_t MAIN2_FLOATS = 2 * BK * A2_LD + 2 * BK * BS_LD;
-    static constexpr size_t EPI_FLOATS = (size_t)BM * CS_LD + 8 * BN * 2;
+    static constexpr size_t EPI_FLOATS = (size_t)BM * CS_LD + (size_t)(NT / (BN / 4)) * BN * 2;  // Cs + red[RL][BN][2]
     static constexpr size_t SMEM_BYTES =
         4 * (EPI_FLOATS > MAIN_FLOATS ? (EPI_FLOATS > MAIN2_FLOATS ? EPI_FLOATS : MAIN2_FLOATS)
                                       : (MAIN_FLOATS > MAIN2_FLOATS ? MAIN_FLOATS : MAIN2_FLOATS));
@@ -205,7 +205,6 @@ __device__ __forceinline__ void reduce_cols(float* red, const float (&s1)[4], co
     constexpr int RL = NT / C4;  // row lanes: 8 (BN=128) or 16 (BN=64)
     const int c4 = tid % C4, rl = tid / C4;
     __syncthreads();
-    // red layout [RL][BN][2] may exceed the 8-lane budget for BN=64 (16 lanes * 64 cols = same float count) -> fits.
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         red[(rl * BN + c4 * 4 + j) * 2 + 0] = s1[j];

@@ -1,0 +1,317 @@
+// Host-side orchestration of a whole MLP stack (SharedMLP / Seq of the reference) in ONE C-ABI call per direction.
+//
+// Python dispatch cost dominated the first fused version (hundreds of tiny torch ops per step just to pad / transpose
+// weights and slice workspaces), so the per-layer sequencing lives here: the caller hands over one descriptor with the
+// raw parameter pointers of the reference modules (weights in their checkpoint layout), one workspace buffer, and gets
+// every kernel of the stack enqueued on the stream: weight packing, per-layer GEMM (+tcgen05 variant), batch-norm
+// finalisation, pooling / activation, and on the way back the BN-backward finalisation, wgrad, dgrad and the
+// un-packing of the weight gradients into the checkpoint layout.  Nothing is allocated and nothing synchronises, so a
+// stack can be captured into a CUDA graph.
+#include <string.h>
+#include "common.cuh"
+#include "../../include/o3d_b200.h"
+
+namespace {
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int r4(int x) { return (x + 3) & ~3; }
+
+// ---- weight packing -----------------------------------------------------------------------------------------
+// src: [cout, cin] row-major (checkpoint layout).  dst wp: [Nw, K] zero padded; wt: [K, Nw] its transpose.
+// xyz_first: src columns are [xyz(3) | feat(c0)] while the kernel rows are [feat(c0) | zeros | dx dy dz 0] (K = c0p + 4).
+__device__ __forceinline__ int src_col(int k, int K, int cin, int xyz_first, int c0) {
+    if (!xyz_first) return k < cin ? k : -1;
+    if (k < c0) return 3 + k;             // feature columns
+    if (k >= K - 4 && k < K - 1) return k - (K - 4);   // dx dy dz
+    return -1;
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int cin, int Nw, int K, int xyz_first, int c0,
+                                   float* __restrict__ wp, float* __restrict__ wt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nw * K) return;
+    const int n = i / K, k = i % K;
+    float v = 0.f;
+    if (n < cout) {
+        const int sc = src_col(k, K, cin, xyz_first, c0);
+        if (sc >= 0) v = src[(size_t)n * cin + sc];
+    }
+    wp[i] = v;
+    wt[(size_t)k * Nw + n] = v;
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int cout, int cin, int K, int xyz_first, int c0,
+                                    float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cout * K) return;
+    const int n = i / K, k = i % K;
+    const int sc = src_col(k, K, cin, xyz_first, c0);
+    if (sc >= 0) dst[(size_t)n * cin + sc] = dwp[i];
+}
+
+__global__ void pad_vec_kernel(const float* __restrict__ src, int n, int npad, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npad) dst[i] = i < n ? src[i] : 0.f;
+}
+
+__global__ void d2f_kernel(const double* __restrict__ src, int n, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+
+__global__ void copy_f_kernel(const float* __restrict__ src, int n, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// ---- workspace plan -------------------------------------------------------------------------------------------
+struct Plan {
+    int n, P, S, rows;
+    int Nw[O3D_MAX_LAYERS], K[O3D_MAX_LAYERS];
+    bool tc_f[O3D_MAX_LAYERS], tc_b[O3D_MAX_LAYERS];
+    // forward (persisted) offsets
+    size_t wp[O3D_MAX_LAYERS], wt[O3D_MAX_LAYERS], bias[O3D_MAX_LAYERS], y[O3D_MAX_LAYERS], vec[O3D_MAX_LAYERS],
+        stat[O3D_MAX_LAYERS], tiles[O3D_MAX_LAYERS];
+    size_t ymax, ymin, arg, sel, ysel, stat_all, stat_bytes, fwd_bytes;
+    // backward (temporary) offsets
+    size_t bstat, bstat_bytes, coef[O3D_MAX_LAYERS], dwp[O3D_MAX_LAYERS], btiles[O3D_MAX_LAYERS], dpool, gbuf[2], bwd_bytes;
+};
+
+bool make_plan(const o3d_stack_t* d, Plan& p) {
+    if (d->n_layers < 1 || d->n_layers > O3D_MAX_LAYERS || d->P < 0 || d->K0 < 4 || (d->K0 & 3)) return false;
+    p.n = d->n_layers; p.P = d->P; p.S = d->S;
+    p.rows = d->S > 0 ? d->P / d->S : d->P;
+    size_t o = 0;
+    for (int l = 0; l < p.n; ++l) {
+        p.Nw[l] = r4(d->cout[l]);
+        p.K[l] = l == 0 ? d->K0 : p.Nw[l - 1];
+        p.tc_f[l] = d->use_tc && p.Nw[l] >= 128 && p.K[l] >= 32 && d->P >= 128;
+        p.tc_b[l] = d->use_tc && p.K[l] >= 128 && p.Nw[l] >= 32 && d->P >= 128;
+    }
+    // statistics block first (one memset)
+    p.stat_all = o;
+    for (int l = 0; l < p.n; ++l) { p.stat[l] = o; o += al(sizeof(double) * 2 * p.Nw[l]); }
+    p.stat_bytes = o - p.stat_all;
+    for (int l = 0; l < p.n; ++l) {
+        p.wp[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]);
+        p.wt[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]);
+        p.bias[l] = o; o += al(sizeof(float) * p.Nw[l]);
+        p.vec[l] = o; o += al(sizeof(float) * 4 * p.Nw[l]);
+        p.tiles[l] = o; if (p.tc_f[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(p.Nw[l], p.K[l]));
+        p.y[l] = o; o += al(sizeof(float) * (size_t)p.P * p.Nw[l]);
+    }
+    const size_t gsz = al(sizeof(float) * (size_t)p.rows * p.Nw[p.n - 1]);
+    p.ymax = o; o += p.S > 0 ? gsz : 0;
+    p.ymin = o; o += p.S > 0 ? gsz : 0;
+    p.arg = o; o += p.S > 0 ? gsz : 0;
+    p.sel = o; o += p.S > 0 ? gsz : 0;
+    p.ysel = o; o += p.S > 0 ? gsz : 0;
+    p.fwd_bytes = o;
+    // backward
+    o = 0;
+    p.bstat = o;
+    for (int l = 0; l < p.n; ++l) o += al(sizeof(double) * 2 * p.Nw[l]);
+    p.bstat_bytes = o;
+    size_t maxk = 0;
+    for (int l = 0; l < p.n; ++l) {
+        p.coef[l] = o; o += al(sizeof(float) * 5 * p.Nw[l]);
+        p.dwp[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]);
+        p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(p.K[l], p.Nw[l]));
+        if ((size_t)p.K[l] > maxk) maxk = p.K[l];
+    }
+    size_t maxn = 0;
+    for (int l = 0; l < p.n; ++l) if ((size_t)p.Nw[l] > maxn) maxn = p.Nw[l];
+    if (maxn > maxk) maxk = maxn;
+    p.dpool = o; o += p.S > 0 ? gsz : 0;
+    for (int i = 0; i < 2; ++i) { p.gbuf[i] = o; o += al(sizeof(float) * (size_t)p.P * maxk); }
+    p.bwd_bytes = o;
+    return true;
+}
+
+inline double* stat_sum(const Plan& p, uint8_t* ws, int l) { return reinterpret_cast<double*>(ws + p.stat[l]); }
+template <class T> inline T* at(uint8_t* ws, size_t off) { return reinterpret_cast<T*>(ws + off); }
+template <class T> inline const T* at(const uint8_t* ws, size_t off) { return reinterpret_cast<const T*>(ws + off); }
+
+}  // namespace
+
+extern "C" long long o3d_stack_workspace_bytes(const o3d_stack_t* d, int backward) {
+    Plan p;
+    if (!d || !make_plan(d, p)) return -1;
+    return (long long)(backward ? p.bwd_bytes : p.fwd_bytes);
+}
+
+extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float* out, int keep_for_backward,
+                                 void* stream) {
+    O3D_REQUIRE(d && x && ws_fwd && out, O3D_ERR_ARG, "o3d_stack_forward: null pointer");
+    Plan p;
+    O3D_REQUIRE(make_plan(d, p), O3D_ERR_ARG, "o3d_stack_forward: bad stack description");
+    O3D_REQUIRE(p.S == 0 || (128 % p.S == 0 && p.P % p.S == 0), O3D_ERR_ARG, "o3d_stack_forward: group size %d", p.S);
+    if (p.P == 0) return O3D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)ws_fwd;
+    if (d->training) O3D_CUDA(cudaMemsetAsync(ws + p.stat_all, 0, p.stat_bytes, st), "o3d_stack_forward: memset");
+    const float* cur = x;
+    int cur_ld = d->K0;
+    const float *in_scale = nullptr, *in_shift = nullptr;
+    int in_relu = 0;
+    const int L = p.n - 1;
+    for (int l = 0; l < p.n; ++l) {
+        const int Nw = p.Nw[l], K = p.K[l], cout = d->cout[l];
+        float* wp = at<float>(ws, p.wp[l]);
+        float* wt = at<float>(ws, p.wt[l]);
+        pack_weight_kernel<<<(Nw * K + 255) / 256, 256, 0, st>>>(d->weight[l], cout, d->cin[l], Nw, K,
+                                                                 l == 0 ? d->xyz_first : 0, d->c0, wp, wt);
+        O3D_CHECK_LAUNCH("o3d_stack_forward: pack_weight");
+        float* bias = nullptr;
+        if (d->bias[l]) {
+            bias = at<float>(ws, p.bias[l]);
+            pad_vec_kernel<<<(Nw + 127) / 128, 128, 0, st>>>(d->bias[l], cout, Nw, bias);
+        }
+        const bool last = l == L, pool = last && p.S > 0;
+        const bool keep_y = !last || keep_for_backward || !pool;
+        float* y = keep_y ? at<float>(ws, p.y[l]) : nullptr;
+        const bool stats = d->training && d->has_bn[l];
+        double* sum = stats ? stat_sum(p, ws, l) : nullptr;
+        double* sumsq = stats ? sum + Nw : nullptr;
+        float* ymax = pool ? at<float>(ws, p.ymax) : nullptr;
+        float* ymin = pool ? at<float>(ws, p.ymin) : nullptr;
+        int32_t* arg = pool ? at<int32_t>(ws, p.arg) : nullptr;
+        int rc;
+        if (p.tc_f[l]) {
+            void* tiles = ws + p.tiles[l];
+            rc = o3d_pw_tc_pretile(wp, K, Nw, K, tiles, stream);
+            if (rc) return rc;
+            rc = o3d_pw_fwd_tc(cur, cur_ld, in_scale, in_shift, in_relu, tiles, bias, p.P, K, cout, y, Nw, sum, sumsq,
+                               pool ? p.S : 0, ymax, ymin, arg, Nw, stream);
+        } else {
+            rc = o3d_pw_fwd(cur, cur_ld, in_scale, in_shift, in_relu, wt, Nw, bias, p.P, K, cout, y, Nw, sum, sumsq,
+                            pool ? p.S : 0, ymax, ymin, arg, Nw, stream);
+        }
+        if (rc) return rc;
+        float* vec = at<float>(ws, p.vec[l]);
+        float *sc = nullptr, *sh = nullptr;
+        if (d->has_bn[l]) {
+            sc = vec; sh = vec + Nw;
+            O3D_CUDA(cudaMemsetAsync(vec, 0, sizeof(float) * 4 * Nw, st), "o3d_stack_forward: memset vec");
+            rc = o3d_bn_fwd_finalize(sum, sumsq, (double)p.P, d->gamma[l], d->beta[l], d->running_mean[l], d->running_var[l],
+                                     d->training ? d->num_batches_tracked[l] : nullptr, d->momentum[l], d->eps[l],
+                                     d->training, cout, sc, sh, vec + 2 * Nw, vec + 3 * Nw, stream);
+            if (rc) return rc;
+        }
+        if (last) {
+            if (pool) {
+                rc = o3d_pool_finalize(ymax, ymin, arg, sc, sh, d->relu[l], p.rows, Nw, Nw, out, Nw,
+                                       keep_for_backward ? at<int32_t>(ws, p.sel) : nullptr,
+                                       keep_for_backward ? at<float>(ws, p.ysel) : nullptr, stream);
+            } else if (d->has_bn[l] || d->relu[l]) {
+                rc = o3d_act_apply(y, Nw, sc, sh, d->relu[l], p.P, Nw, out, Nw, stream);
+            } else {
+                O3D_CUDA(cudaMemcpyAsync(out, y, sizeof(float) * (size_t)p.P * Nw, cudaMemcpyDeviceToDevice, st),
+                         "o3d_stack_forward: copy out");
+                rc = O3D_OK;
+            }
+            if (rc) return rc;
+        }
+        cur = y; cur_ld = Nw; in_scale = sc; in_shift = sh; in_relu = d->relu[l];
+    }
+    return O3D_OK;
+}
+
+extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const void* ws_fwd, void* ws_bwd, const float* out,
+                                  const float* dout, float* dx, void* stream) {
+    O3D_REQUIRE(d && x && ws_fwd && ws_bwd && out && dout, O3D_ERR_ARG, "o3d_stack_backward: null pointer");
+    Plan p;
+    O3D_REQUIRE(make_plan(d, p), O3D_ERR_ARG, "o3d_stack_backward: bad stack description");
+    if (p.P == 0) return O3D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* wf = (const uint8_t*)ws_fwd;
+    uint8_t* wb = (uint8_t*)ws_bwd;
+    O3D_CUDA(cudaMemsetAsync(wb + p.bstat, 0, p.bstat_bytes, st), "o3d_stack_backward: memset");
+    auto s1 = [&](int l) { size_t o = p.bstat; for (int i = 0; i < l; ++i) o += al(sizeof(double) * 2 * p.Nw[i]); return at<double>(wb, o); };
+    const int L = p.n - 1;
+    const int NwL = p.Nw[L];
+    const float* yL = at<float>(wf, p.y[L]);
+    const float* g = nullptr;      // dense gradient entering layer l's BN/ReLU
+    float* dpool = nullptr;
+    int rc;
+    if (p.S > 0) {
+        dpool = at<float>(wb, p.dpool);
+        rc = o3d_pool_bwd_prep(dout, NwL, out, NwL, at<float>(wf, p.ysel), d->relu[L], p.rows, NwL, NwL, dpool, s1(L),
+                               s1(L) + NwL, stream);
+        if (rc) return rc;
+    } else if (d->has_bn[L] || d->relu[L]) {
+        float* gb = at<float>(wb, p.gbuf[0]);
+        rc = o3d_dense_bwd_prep(dout, NwL, out, NwL, yL, NwL, d->relu[L], p.P, NwL, gb, NwL, s1(L), s1(L) + NwL, stream);
+        if (rc) return rc;
+        g = gb;
+    } else {
+        g = dout;
+        if (d->bias[L]) {
+            rc = o3d_dense_bwd_prep(dout, NwL, nullptr, 0, nullptr, 0, 0, p.P, NwL, nullptr, 0, s1(L), nullptr, stream);
+            if (rc) return rc;
+        }
+    }
+    int gsel = (g == at<float>(wb, p.gbuf[0])) ? 1 : 0;   // next free ping-pong buffer
+    for (int l = L; l >= 0; --l) {
+        const int Nl = p.Nw[l], K = p.K[l], cout = d->cout[l];
+        float* coef = at<float>(wb, p.coef[l]);
+        const float *a = nullptr, *b = nullptr, *cc = nullptr;
+        const float* vec = at<float>(wf, p.vec[l]);
+        if (d->has_bn[l]) {
+            O3D_CUDA(cudaMemsetAsync(coef, 0, sizeof(float) * 5 * Nl, st), "o3d_stack_backward: memset coef");
+            rc = o3d_bn_bwd_finalize(s1(l), s1(l) + Nl, (double)p.P, d->gamma[l], vec + 2 * Nl, vec + 3 * Nl, d->training,
+                                     cout, coef, coef + Nl, coef + 2 * Nl, coef + 3 * Nl, coef + 4 * Nl, stream);
+            if (rc) return rc;
+            a = coef; b = coef + Nl; cc = coef + 2 * Nl;
+            if (d->d_gamma[l]) copy_f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(coef + 3 * Nl, cout, d->d_gamma[l]);
+            if (d->d_beta[l]) copy_f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(coef + 4 * Nl, cout, d->d_beta[l]);
+            if (d->d_bias[l]) O3D_CUDA(cudaMemsetAsync(d->d_bias[l], 0, sizeof(float) * cout, st), "d_bias");  // BN removes the mean
+        } else if (d->d_bias[l]) {
+            d2f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(s1(l), cout, d->d_bias[l]);
+        }
+        const bool pooled = (l == L && p.S > 0);
+        const float* gl = pooled ? nullptr : g;
+        const float* yl = a ? at<float>(wf, p.y[l]) : nullptr;
+        const float* dpl = pooled ? dpool : nullptr;
+        const int32_t* sel = pooled ? at<int32_t>(wf, p.sel) : nullptr;
+        const int Sg = pooled ? p.S : 0;
+        // input operand of this layer
+        const float* xin = l == 0 ? x : at<float>(wf, p.y[l - 1]);
+        const float* pvec = l == 0 ? nullptr : at<float>(wf, p.vec[l - 1]);
+        const int Kp = K;
+        const float* psc = (l > 0 && d->has_bn[l - 1]) ? pvec : nullptr;
+        const float* psh = (l > 0 && d->has_bn[l - 1]) ? pvec + Kp : nullptr;
+        const int prelu = l > 0 ? d->relu[l - 1] : 0;
+        if (d->d_weight[l]) {
+            float* dwp = at<float>(wb, p.dwp[l]);
+            O3D_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)Nl * K, st), "o3d_stack_backward: memset dW");
+            rc = o3d_pw_wgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, K, dwp, K, stream);
+            if (rc) return rc;
+            unpack_wgrad_kernel<<<(cout * K + 255) / 256, 256, 0, st>>>(dwp, cout, d->cin[l], K, l == 0 ? d->xyz_first : 0,
+                                                                        d->c0, d->d_weight[l]);
+            O3D_CHECK_LAUNCH("o3d_stack_backward: unpack_wgrad");
+        }
+        if (l > 0 || dx) {
+            float* gout = l > 0 ? at<float>(wb, p.gbuf[gsel]) : dx;
+            const bool mask = l > 0 && (d->has_bn[l - 1] || d->relu[l - 1]);
+            const bool want = l > 0 && (d->has_bn[l - 1] || d->bias[l - 1] != nullptr);
+            const float* yprev = mask ? at<float>(wf, p.y[l - 1]) : nullptr;
+            double* ps1 = want ? s1(l - 1) : nullptr;
+            double* ps2 = want ? s1(l - 1) + K : nullptr;
+            if (p.tc_b[l]) {
+                void* tiles = wb + p.btiles[l];
+                rc = o3d_pw_tc_pretile(at<float>(wf, p.wt[l]), Nl, K, Nl, tiles, stream);
+                if (rc) return rc;
+                rc = o3d_pw_dgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, tiles, p.P, Nl, K, gout, K, yprev, K, psc, psh,
+                                     prelu, ps1, ps2, stream);
+            } else {
+                rc = o3d_pw_dgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, at<float>(wf, p.wp[l]), K, p.P, Nl, K, gout, K,
+                                  yprev, K, psc, psh, prelu, ps1, ps2, stream);
+            }
+            if (rc) return rc;
+            g = gout;
+            gsel ^= 1;
+        }
+    }
+    return O3D_OK;
+}

@@ -12,11 +12,13 @@ on channels-last activations; normalised activations, the BN backward and the Re
 operand loaders / epilogues of the GEMMs.  Parameters stay in the reference's modules (same names, same
 state-dict), torch is used for buffers and the autograd graph only.
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, ops
+from . import _lib, ops, runtime
 from .pointnet2.utils import pointnet2_utils
 
 _call = ops._call
@@ -76,210 +78,113 @@ def parse_stack(module):
 class _Meta:
     """Static description of one stack invocation (python objects only)."""
 
-    def __init__(self, specs, S, training):
+    def __init__(self, specs, S, training, xyz_first=False, c0=0):
+        if len(specs) > _lib.MAX_LAYERS:
+            raise RuntimeError(f"fused MLP stack: at most {_lib.MAX_LAYERS} layers")
         self.n = len(specs)
         self.S = int(S)
         self.training = bool(training)
-        self.has_bias = [s.bias is not None for s in specs]
-        self.has_bn = [s.bn is not None for s in specs]
-        self.relu = [bool(s.relu) for s in specs]
+        self.xyz_first = bool(xyz_first)
+        self.c0 = int(c0)
         self.bns = [s.bn for s in specs]
+        self.relu = [bool(s.relu) for s in specs]
         self.cout = [s.weight.shape[0] for s in specs]
+        self.cin = [s.weight.numel() // s.weight.shape[0] for s in specs]
+
+
+def _describe(meta, P, K0, params):
+    d = _lib.StackDesc()
+    d.n_layers, d.P, d.K0, d.S = meta.n, P, K0, meta.S
+    d.training, d.use_tc = int(meta.training), int(runtime.tc_enabled())
+    d.xyz_first, d.c0 = int(meta.xyz_first), meta.c0
+    for l in range(meta.n):
+        W, b, g, be = params[4 * l:4 * l + 4]
+        bn = meta.bns[l]
+        d.cin[l], d.cout[l], d.relu[l], d.has_bn[l] = meta.cin[l], meta.cout[l], int(meta.relu[l]), int(bn is not None)
+        d.weight[l], d.bias[l], d.gamma[l], d.beta[l] = W.data_ptr(), _ptr(b), _ptr(g), _ptr(be)
+        if bn is not None:
+            d.momentum[l] = 0.1 if bn.momentum is None else bn.momentum
+            d.eps[l] = bn.eps
+            if bn.track_running_stats and bn.running_mean is not None:
+                d.running_mean[l], d.running_var[l] = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                d.num_batches_tracked[l] = bn.num_batches_tracked.data_ptr()
+    return d
 
 
 class _MLPStackFn(torch.autograd.Function):
-    """x (P, K0p) channels-last fp32; per layer W (Cout, Cin) 2-D, bias|None, gamma|None, beta|None."""
+    """x (P, K0) channels-last fp32; per layer: weight (checkpoint layout), bias|None, gamma|None, beta|None."""
 
     @staticmethod
     def forward(ctx, meta, x, *params):
-        dev = x.device
         P, K0 = x.shape
-        n = meta.n
-        Ws, bs, gs, betas = params[0::4], params[1::4], params[2::4], params[3::4]
-        S = meta.S
+        for t in params:
+            if t is not None and not t.is_contiguous():
+                raise RuntimeError("fused MLP stack: parameters must be contiguous")
+        d = _describe(meta, P, K0, params)
+        L = _lib.lib()
         need_grad = any(ctx.needs_input_grad)
-        ctx.wshapes = meta.wshapes
-        st = _stream()
-        nws = [_r4(c) for c in meta.cout]
-        kin = [K0] + nws[:-1]
-        # one zeroed fp64 workspace for all batch statistics
-        stat = torch.zeros(2 * sum(nws), dtype=torch.float64, device=dev) if meta.training and any(meta.has_bn) else None
-        vec = torch.zeros(4 * sum(nws), dtype=torch.float32, device=dev)  # scale | shift | mean | invstd per layer
-        Wp, ys, scales, shifts, means, invstds = [], [], [], [], [], []
-        cur, cur_ld, in_scale, in_shift, in_relu = x, K0, None, None, 0
-        so = vo = 0
-        pooled = None
-        for l in range(n):
-            Nw, K, Cout = nws[l], kin[l], meta.cout[l]
-            W = Ws[l]
-            wp = torch.zeros(Nw, K, dtype=torch.float32, device=dev)
-            wp[:Cout, :W.shape[1]] = W
-            wt = wp.t().contiguous()
-            bias = None
-            if bs[l] is not None:
-                bias = torch.zeros(Nw, dtype=torch.float32, device=dev)
-                bias[:Cout] = bs[l]
-            last = l == n - 1
-            pool_here = last and S > 0
-            keep_y = (not last) or need_grad or (not pool_here)   # inference skips the last raw tensor when pooling
-            y = torch.empty(P, Nw, dtype=torch.float32, device=dev) if keep_y else None
-            use_stats = meta.training and meta.has_bn[l]
-            sm = stat[so:so + Nw] if use_stats else None
-            sq = stat[so + Nw:so + 2 * Nw] if use_stats else None
-            if pool_here:
-                G = P // S
-                ymax = torch.empty(G, Nw, dtype=torch.float32, device=dev)
-                ymin = torch.empty(G, Nw, dtype=torch.float32, device=dev)
-                arg = torch.empty(G, Nw, dtype=torch.int32, device=dev)
-            else:
-                G, ymax, ymin, arg = 0, None, None, None
-            _call("o3d_pw_fwd", cur.data_ptr(), cur_ld, _ptr(in_scale), _ptr(in_shift), int(in_relu), wt.data_ptr(), Nw,
-                  _ptr(bias), P, K, Cout, _ptr(y), Nw, _ptr(sm), _ptr(sq), S if pool_here else 0, _ptr(ymax), _ptr(ymin),
-                  _ptr(arg), Nw, st)
-            sc = sh = mu = istd = None
-            if meta.has_bn[l]:
-                bn = meta.bns[l]
-                sc, sh = vec[vo:vo + Nw], vec[vo + Nw:vo + 2 * Nw]
-                mu, istd = vec[vo + 2 * Nw:vo + 3 * Nw], vec[vo + 3 * Nw:vo + 4 * Nw]
-                mom = bn.momentum if bn.momentum is not None else 0.1
-                track = bn.track_running_stats and bn.running_mean is not None
-                _call("o3d_bn_fwd_finalize", _ptr(sm), _ptr(sq), float(P), _ptr(gs[l]), _ptr(betas[l]),
-                      _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
-                      _ptr(bn.num_batches_tracked) if (track and meta.training) else None, float(mom), float(bn.eps),
-                      int(meta.training), Cout, sc.data_ptr(), sh.data_ptr(), mu.data_ptr(), istd.data_ptr(), st)
-            Wp.append(wp); ys.append(y); scales.append(sc); shifts.append(sh); means.append(mu); invstds.append(istd)
-            cur, cur_ld, in_scale, in_shift, in_relu = y, Nw, sc, sh, int(meta.relu[l])
-            so += 2 * Nw
-            vo += 4 * Nw
-        # ---- output of the last layer
-        Nw, Cout = nws[-1], meta.cout[-1]
-        sel = ysel = None
-        if S > 0:
-            out = torch.empty(G, Nw, dtype=torch.float32, device=dev)
-            sel = torch.empty(G, Nw, dtype=torch.int32, device=dev) if need_grad else None
-            ysel = torch.empty(G, Nw, dtype=torch.float32, device=dev) if need_grad else None
-            _call("o3d_pool_finalize", ymax.data_ptr(), ymin.data_ptr(), arg.data_ptr(), _ptr(scales[-1]),
-                  _ptr(shifts[-1]), int(meta.relu[-1]), G, Nw, Nw, out.data_ptr(), Nw, _ptr(sel), _ptr(ysel), st)
-        elif meta.has_bn[-1] or meta.relu[-1]:
-            out = torch.empty(P, Nw, dtype=torch.float32, device=dev)
-            _call("o3d_act_apply", ys[-1].data_ptr(), Nw, _ptr(scales[-1]), _ptr(shifts[-1]), int(meta.relu[-1]), P, Nw,
-                  out.data_ptr(), Nw, st)
-        else:
-            out = ys[-1]
-        ctx.meta = meta
-        ctx.dims = (P, K0, nws, kin)
-        ctx.saved = (x, Wp, ys, scales, shifts, means, invstds, sel, ysel, out, gs, vec)
+        nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 0)
+        if nbytes < 0:
+            raise RuntimeError("fused MLP stack: invalid stack description")
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.device)
+        rows = P // meta.S if meta.S > 0 else P
+        Nw, Cout = _r4(meta.cout[-1]), meta.cout[-1]
+        out = torch.empty(rows, Nw, dtype=torch.float32, device=x.device)
+        ops.LAUNCHES += 3 * meta.n + 1
+        _lib.check(L.o3d_stack_forward(ctypes.byref(d), x.data_ptr(), ws.data_ptr(), out.data_ptr(), int(need_grad),
+                                       _stream()), "o3d_stack_forward")
+        if need_grad:
+            ctx.meta, ctx.desc, ctx.params = meta, d, params
+            ctx.save_for_backward(x, ws, out)
         return out if Nw == Cout else out[:, :Cout]
 
     @staticmethod
     def backward(ctx, dout):
-        meta = ctx.meta
-        P, K0, nws, kin = ctx.dims
-        x, Wp, ys, scales, shifts, means, invstds, sel, ysel, out, gs, _vec = ctx.saved
-        n, S = meta.n, meta.S
-        dev = x.device
-        st = _stream()
-        Nw = nws[-1]
-        rows = P // S if S > 0 else P
-        # padded, contiguous upstream gradient
+        meta, d, params = ctx.meta, ctx.desc, ctx.params
+        x, ws, out = ctx.saved_tensors
+        P, K0 = x.shape
+        Nw = out.shape[1]
         if dout.shape[1] != Nw or not dout.is_contiguous():
-            d = torch.zeros(rows, Nw, dtype=torch.float32, device=dev)
-            d[:, :dout.shape[1]] = dout
-            dout = d
-        stat = torch.zeros(2 * sum(nws), dtype=torch.float64, device=dev)     # s1 | s2y per layer
-        coef = torch.zeros(5 * sum(nws), dtype=torch.float32, device=dev)     # a | b | cc | dgamma | dbeta per layer
-        offs, o = [], 0
-        for w in nws:
-            offs.append(o)
-            o += w
-        s1 = [stat[2 * offs[l]:2 * offs[l] + nws[l]] for l in range(n)]
-        s2 = [stat[2 * offs[l] + nws[l]:2 * offs[l] + 2 * nws[l]] for l in range(n)]
-
-        def cf(l, j):
-            return coef[5 * offs[l] + j * nws[l]:5 * offs[l] + (j + 1) * nws[l]]
-
-        # ---- gradient entering the last layer's BN/ReLU (or the plain output)
-        L = n - 1
-        g = dpool = None
-        if S > 0:
-            dpool = torch.empty(rows, Nw, dtype=torch.float32, device=dev)
-            _call("o3d_pool_bwd_prep", dout.data_ptr(), Nw, out.data_ptr(), Nw, ysel.data_ptr(), int(meta.relu[L]), rows,
-                  Nw, Nw, dpool.data_ptr(), s1[L].data_ptr(), s2[L].data_ptr(), st)
-        elif meta.has_bn[L] or meta.relu[L]:
-            g = torch.empty(P, Nw, dtype=torch.float32, device=dev)
-            _call("o3d_dense_bwd_prep", dout.data_ptr(), Nw, out.data_ptr(), Nw, ys[L].data_ptr(), Nw, int(meta.relu[L]), P,
-                  Nw, g.data_ptr(), Nw, s1[L].data_ptr(), s2[L].data_ptr(), st)
-        else:
-            g = dout
-            if meta.has_bias[L]:
-                _call("o3d_dense_bwd_prep", dout.data_ptr(), Nw, None, 0, None, 0, 0, P, Nw, None, 0, s1[L].data_ptr(),
-                      None, st)
-        grads = [None] * (4 * n)
-        dx = None
-        need_dx = ctx.needs_input_grad[1]
-        for l in range(L, -1, -1):
-            Nl, K = nws[l], kin[l]
-            a = b = cc = None
-            if meta.has_bn[l]:
-                a, b, cc = cf(l, 0), cf(l, 1), cf(l, 2)
-                _call("o3d_bn_bwd_finalize", s1[l].data_ptr(), s2[l].data_ptr(), float(P), _ptr(gs[l]), means[l].data_ptr(),
-                      invstds[l].data_ptr(), int(meta.training), meta.cout[l], a.data_ptr(), b.data_ptr(), cc.data_ptr(),
-                      cf(l, 3).data_ptr(), cf(l, 4).data_ptr(), st)
-                grads[4 * l + 2] = cf(l, 3)[:meta.cout[l]]
-                grads[4 * l + 3] = cf(l, 4)[:meta.cout[l]]
-                if meta.has_bias[l]:
-                    grads[4 * l + 1] = torch.zeros(meta.cout[l], dtype=torch.float32, device=dev)  # BN removes the mean
-            elif meta.has_bias[l]:
-                grads[4 * l + 1] = s1[l][:meta.cout[l]].float()
-            pooled_mode = (l == L and S > 0)
-            dy_args = (_ptr(None if pooled_mode else g), Nl, _ptr(ys[l]) if a is not None else None, Nl, _ptr(a), _ptr(b),
-                       _ptr(cc), _ptr(dpool) if pooled_mode else None, _ptr(sel) if pooled_mode else None,
-                       S if pooled_mode else 0, Nl)
-            # wgrad: dW = dY^T * A(x_l)
-            xin = x if l == 0 else ys[l - 1]
-            psc = None if l == 0 else scales[l - 1]
-            psh = None if l == 0 else shifts[l - 1]
-            prelu = 0 if l == 0 else int(meta.relu[l - 1])
-            dw = torch.zeros(Nl, K, dtype=torch.float32, device=dev)
-            _call("o3d_pw_wgrad", *dy_args, xin.data_ptr(), K, _ptr(psc), _ptr(psh), prelu, P, Nl, K, dw.data_ptr(), K, st)
-            grads[4 * l] = dw[:meta.cout[l], :ctx.wshapes[l]]
-            # dgrad: gradient w.r.t. this layer's input, masked by the previous layer's ReLU
-            if l > 0 or need_dx:
-                gout = torch.empty(P, K, dtype=torch.float32, device=dev)
-                if l > 0:
-                    want_stats = meta.has_bn[l - 1] or meta.has_bias[l - 1]
-                    mask = meta.has_bn[l - 1] or meta.relu[l - 1]
-                    _call("o3d_pw_dgrad", *dy_args, Wp[l].data_ptr(), K, P, Nl, K, gout.data_ptr(), K,
-                          ys[l - 1].data_ptr() if mask else None, K, _ptr(psc), _ptr(psh), prelu,
-                          s1[l - 1].data_ptr() if want_stats else None, s2[l - 1].data_ptr() if want_stats else None, st)
-                    g = gout
+            dpad = torch.zeros(out.shape, dtype=torch.float32, device=x.device)
+            dpad[:, :dout.shape[1]] = dout
+            dout = dpad
+        grads = [None] * (4 * meta.n)
+        fields = (d.d_weight, d.d_bias, d.d_gamma, d.d_beta)
+        for l in range(meta.n):
+            for j in range(4):
+                t = params[4 * l + j]
+                if t is not None and ctx.needs_input_grad[2 + 4 * l + j]:
+                    gt = torch.empty_like(t)
+                    grads[4 * l + j] = gt
+                    fields[j][l] = gt.data_ptr()
                 else:
-                    _call("o3d_pw_dgrad", *dy_args, Wp[l].data_ptr(), K, P, Nl, K, gout.data_ptr(), K, None, 0, None, None,
-                          0, None, None, st)
-                    dx = gout
+                    fields[j][l] = None
+        dx = torch.empty(P, K0, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[1] else None
+        L = _lib.lib()
+        nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 1)
+        wb = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.device)
+        ops.LAUNCHES += 5 * meta.n + 1
+        _lib.check(L.o3d_stack_backward(ctypes.byref(d), x.data_ptr(), ws.data_ptr(), wb.data_ptr(), out.data_ptr(),
+                                        dout.data_ptr(), _ptr(dx), _stream()), "o3d_stack_backward")
         return (None, dx, *grads)
 
 
-def mlp_stack(x2d, specs, S=0, training=True, weights=None):
+def mlp_stack(x2d, specs, S=0, training=True, xyz_first=False, c0=0):
     """Run a stack on a channels-last matrix.
 
-    x2d      (P, K0) fp32, contiguous, K0 % 4 == 0 (zero-padded input channels)
-    specs    list of _LayerSpec (parameters of the reference modules)
-    S        pooling group size over consecutive positions (0 = dense output)
-    weights  optional list of 2-D (Cout, Cin<=K) tensors replacing spec.weight (re-ordered / padded input columns)
-    returns  (P or P//S, Cout_last)
+    x2d        (P, K0) fp32, contiguous, K0 % 4 == 0 (zero-padded input channels)
+    specs      list of _LayerSpec (parameters of the reference modules, checkpoint layout)
+    S          pooling group size over consecutive positions (0 = dense output); must divide 128 and P
+    xyz_first  layer-0 weight columns are [xyz(3) | features(c0)] while rows are [features | dx dy dz 0]
+    returns    (P or P//S, Cout_last)
     """
     if not x2d.is_cuda:
         raise RuntimeError("open3dsot_b200.fused: CUDA tensors required (there is no CPU path)")
     assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32 and x2d.shape[1] % 4 == 0
-    meta = _Meta(specs, S, training)
+    meta = _Meta(specs, S, training, xyz_first, c0)
     params = []
-    wshapes = []
-    for i, s in enumerate(specs):
-        W = weights[i] if weights is not None and weights[i] is not None else s.weight.reshape(s.weight.shape[0], -1)
-        wshapes.append(W.shape[1])
-        params += [W, s.bias, s.bn.weight if s.bn is not None else None, s.bn.bias if s.bn is not None else None]
-    meta.wshapes = wshapes
+    for s in specs:
+        params += [s.weight, s.bias, s.bn.weight if s.bn is not None else None, s.bn.bias if s.bn is not None else None]
     return _MLPStackFn.apply(meta, x2d, *params)
 
 
@@ -330,18 +235,11 @@ def sa_forward(sa, xyz, features, sample_idxs):
         grouped, _idx = pointnet2_utils.query_and_group_cl(xyz, new_xyz, feat_cl, grouper.radius, S,
                                                            grouper.normalize_xyz)
         specs = parse_stack(mlp)
-        W0 = specs[0].weight.reshape(specs[0].weight.shape[0], -1)
-        # reference channel order is [xyz(3), features(C)]; kernel rows are [features(Cp) | dx dy dz 0]
-        if grouper.use_xyz:
-            wx, wf = W0[:, :3], W0[:, 3:]
-        else:
-            wx, wf = W0.new_zeros(W0.shape[0], 3), W0
-        parts = [wf]
-        if Cp > C:
-            parts.append(W0.new_zeros(W0.shape[0], Cp - C))
-        parts.append(wx)
-        packed = torch.cat(parts, dim=1) if len(parts) > 1 else wx
-        pooled = mlp_stack(grouped.view(B * npoint * S, Cp + 4), specs, S, sa.training, weights=[packed] + [None] * (len(specs) - 1))
+        if not grouper.use_xyz:
+            raise RuntimeError("fused SA layer expects use_xyz=True (every shipped model does)")
+        # the reference's channel order is [xyz(3), features(C)]; kernel rows are [features(Cp) | dx dy dz 0]:
+        # the re-ordering of the first conv's columns happens inside o3d_stack_forward (xyz_first)
+        pooled = mlp_stack(grouped.view(B * npoint * S, Cp + 4), specs, S, sa.training, xyz_first=True, c0=C)
         outs.append(from_channels_last(pooled.reshape(B, npoint, pooled.shape[1])))
     return new_xyz, outs
 

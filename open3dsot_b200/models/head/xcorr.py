@@ -27,7 +27,7 @@ class P2B_XCorr(BaseXCorr):
 
     def forward(self, template_feature, search_feature, template_xyz):
         """template_feature (B,f,M), search_feature (B,f,N), template_xyz (B,M,3) -> (B,out,N)."""
-        if runtime.fused_enabled():
+        if runtime.fused_enabled() and 128 % template_feature.size(2) == 0:   # group pooling needs n1 | 128
             from ... import fused
             return fused.p2b_xcorr_forward(self, template_feature, search_feature, template_xyz)
         B, f, n1 = template_feature.shape
@@ -60,7 +60,7 @@ class BoxAwareXCorr(BaseXCorr):
                 search_bc=None):
         """template_feature (B,f,M), search_feature (B,f,N), template_xyz (B,M,3), template_bc (B,M,9),
         search_bc (B,N,9) -> (B,out,N)."""
-        if runtime.fused_enabled() and not (self.use_search_bc or self.use_search_feature):
+        if runtime.fused_enabled() and 128 % self.k == 0 and not (self.use_search_bc or self.use_search_feature):
             from ... import fused
             return fused.boxaware_xcorr_forward(self, template_feature, search_feature, template_xyz, template_bc,
                                                 search_bc)

@@ -5,6 +5,18 @@ import os
 _FUSED = os.environ.get("O3D_FUSED", "1") != "0"
 
 
+_TC = os.environ.get("O3D_TC", "0") != "0"  # tcgen05 3xTF32 GEMM core for the point-wise layers
+
+
+def tc_enabled() -> bool:
+    return _TC
+
+
+def set_tc(flag: bool) -> None:
+    global _TC
+    _TC = bool(flag)
+
+
 def fused_enabled() -> bool:
     return _FUSED
 

@@ -118,3 +118,44 @@ def test_running_stats_follow_torch_batchnorm():
     assert rel(specs[0].bn.running_mean, ref.running_mean) < 1e-5
     assert rel(specs[0].bn.running_var, ref.running_var) < 1e-5
     assert int(specs[0].bn.num_batches_tracked) == 1
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 core
+TC_CASES = [
+    ("tc_sa2", [132, 128, 128, 256], 32 * 64, 32),
+    ("tc_sa3", [260, 256, 256, 256], 32 * 37, 32),      # ragged P (1184 = 9.25 tiles), K = 260 (9 k-blocks, tail)
+    ("tc_bax", [268, 256, 256, 256], 4 * 160, 4),
+    ("tc_dense", [64, 128, 256], 300, 0),
+]
+
+
+@pytest.mark.parametrize("name,chans,P,S", TC_CASES)
+def test_tensor_core_stack_matches_fp64_reference(name, chans, P, S):
+    """tcgen05 3xTF32 forward + dgrad against the fp64 statement: same 1e-4 bar as the exact-fp32 kernels."""
+    from open3dsot_b200 import runtime
+    torch.manual_seed(3)
+    mod = pt.SharedMLP(list(chans), bn=True)
+    randomise(mod, 11)
+    mod = mod.cuda().train()
+    specs = fused.parse_stack(mod)
+    x = torch.randn(P, chans[0], device="cuda")
+    x[:, -1] = 0
+    x1 = x.clone().requires_grad_(True)
+    old = runtime.tc_enabled()
+    runtime.set_tc(True)
+    try:
+        out = fused.mlp_stack(x1, specs, S, True)
+        x2 = x.clone().requires_grad_(True)
+        want = reference_stack(x2, specs, S, True)
+        assert rel(out, want) < RTOL
+        go = torch.randn_like(want)
+        params = [p for p in mod.parameters()]
+        g_ref = torch.autograd.grad(want, [x2] + params, go, allow_unused=True)
+        g_out = torch.autograd.grad(out, [x1] + params, go.float(), allow_unused=True)
+    finally:
+        runtime.set_tc(old)
+    scale = max(float(g.double().norm()) for g in g_ref if g is not None)
+    for gn, gr in zip(g_out, g_ref):
+        if gr is None:
+            continue
+        assert float((gn.double() - gr.double()).norm()) < 2e-4 * max(float(gr.double().norm()), 1e-3 * scale)
