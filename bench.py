@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=None, help="override O3D_FUSED (1 = fused kernels, 0 = composed)")
+    ap.add_argument("--tc", type=int, default=None, help="override O3D_TC (0 = CUDA cores, 1 = tcgen05 fwd+dgrad, 3 = + wgrad)")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
     return ap.parse_args()
 
 
@@ -184,6 +186,8 @@ def run_ours(args):
 
     if args.fused is not None:
         runtime.set_fused(bool(args.fused))
+    if args.tc is not None:
+        runtime.set_tc(args.tc)
     rank, world, local = ddp.init_distributed()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     dev = torch.device("cuda", local)
@@ -194,10 +198,8 @@ def run_ours(args):
     cfg = load_config(CFG_FILE, {"batch_size": args.batch})
     torch.manual_seed(0)
     net = get_model(cfg.net_model)(cfg).to(dev).train()
-    flat = ddp.FlatParams(net)
-    ddp.broadcast_parameters(flat, net)
-    opt = torch.optim.Adam([flat.flat], lr=cfg.lr, betas=(0.5, 0.999), eps=1e-6, weight_decay=cfg.wd, fused=True)
-    flat.flat.grad = flat.grad
+    from open3dsot_b200.engine import TrainStep
+    eng = TrainStep(net, lr=cfg.lr, weight_decay=cfg.wd, use_graph=not args.no_graph, warmup=2)
 
     # distinct host batches (pinned), one device-resident copy of each
     n_batches = 4
@@ -207,25 +209,19 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
-    def step(batch):
-        flat.zero_grad()
-        loss = net.training_step(batch, 0)
-        loss.backward()
-        ddp.allreduce_gradients(flat)
-        opt.step()
-        return loss
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step({k: v.clone() for k, v in resident[i % n_batches].items()})
+    ops.LAUNCHES = 0
+    eng.step(resident[0])                                       # eager: counts the kernels of one step
+    launches_per_step = ops.LAUNCHES
+    for i in range(max(args.warmup, 3) + 3):                    # includes graph capture when enabled
+        eng.step(resident[i % n_batches])
     barrier()
 
     # ---- device-resident timing
-    ops.LAUNCHES = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -234,13 +230,12 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(float(i))                                   # evict L2; not timed
-        batch = {k: v.clone() for k, v in resident[i % n_batches].items()}
         evs[i][0].record()
-        step(batch)
+        eng.step(resident[i % n_batches])
         evs[i][1].record()
     barrier()
     wall = time.perf_counter() - t_wall0
-    launches = ops.LAUNCHES
+    launches = launches_per_step * args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -255,7 +250,7 @@ def run_ours(args):
     last = 0.0
     for i in range(args.steps):
         batch = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
-        last = float(step(batch).item())                       # D2H read of the loss (4 bytes) + host sync
+        last = float(eng.step(batch).item())                   # D2H read of the loss (4 bytes) + host sync
     e1.record()
     barrier()
     e2e_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
@@ -279,8 +274,11 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                        "mode": "fused" if runtime.fused_enabled() else "composed",
+                       "gemm_core": {0: "cuda-core-fp32", 1: "tcgen05-3xTF32 fwd+dgrad, cuda-core wgrad",
+                                     3: "tcgen05-3xTF32 fwd+dgrad+wgrad"}.get(runtime.tc_level(), str(runtime.tc_level())),
+                       "cuda_graph": not args.no_graph,
                        "l2": "256 MiB flush write between timed steps, excluded from timing",
-                       "optimizer": "Adam(0.5,0.999) on the flat parameter bucket", "last_loss": last},
+                       "optimizer": "Adam(0.5,0.999), one kernel over the flat parameter bucket", "last_loss": last},
             "clocks": clocks, "gpu_launches": launches, "wall_s_timed_region": wall,
             "e2e": {"value": pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / args.steps * 1e3},

@@ -222,6 +222,17 @@ int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float*
 int o3d_stack_backward(const o3d_stack_t* d, const float* x, const void* ws_fwd, void* ws_bwd, const float* out,
                        const float* dout, float* dx, void* stream);
 
+/* wgrad on the tensor core (MN-major SWIZZLE_128B operands, split over positions, fp32 RED into dw). */
+int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
+                    const float* dpool, const int32_t* sel, int S, int ldp, const float* x, int ldx,
+                    const float* in_scale, const float* in_shift, int in_relu, int P, int Cout, int Cin, float* dw,
+                    int lddw, void* stream);
+
+/* Adam over a flat fp32 parameter bucket (torch.optim.Adam semantics; the reference uses betas (0.5, 0.999),
+ * eps 1e-6: models/base_model.py:28-36).  state = device float[2] {step count (incremented by the call), lr}.  */
+int o3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                  float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

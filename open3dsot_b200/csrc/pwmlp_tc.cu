@@ -33,9 +33,6 @@ constexpr int TC_K = 32;        // tf32 elements per k-block = 128 bytes per row
 constexpr int TC_STAGES = 3;
 constexpr int TILE_BYTES = TC_M * TC_K * 4;            // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;            // Whi | Wlo | Xhi | Xlo
-constexpr int TC_THREADS = 384;
-constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t TMEM_COLS = 256;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -107,51 +104,69 @@ __device__ __forceinline__ float4 lo_part(const float4& v) {
 __device__ __forceinline__ float4 ld4g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // ---- operand descriptions (same semantics as ActIn / DyIn in pwmlp.cu) --------------------------------------
+// `prep(k)` fetches the per-channel coefficients of the thread's 4 channels once per k-block; `row(p)` then costs one
+// (forward) or two (dgrad) 16-byte loads.
 struct TcAct {
     const float* x; int ld; const float* scale; const float* shift; int relu;
-    __device__ __forceinline__ float4 load(int p, int P, int k, int K) const {
+    struct Coef { float4 s, t; bool on; };
+    __device__ __forceinline__ Coef prep(int k, int K) const {
+        Coef c;
+        c.on = k < K;
+        c.s = make_float4(1.f, 1.f, 1.f, 1.f);
+        c.t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c.on && scale) { c.s = ld4g(scale + k); c.t = ld4g(shift + k); }
+        return c;
+    }
+    __device__ __forceinline__ float4 row(const Coef& c, int p, int P, int k) const {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < P && k < K) {
+        if (c.on && p < P) {
             v = ld4g(x + (size_t)p * ld + k);
-            if (scale) {
-                const float4 s = ld4g(scale + k), t = ld4g(shift + k);
-                v.x = fmaf(v.x, s.x, t.x); v.y = fmaf(v.y, s.y, t.y); v.z = fmaf(v.z, s.z, t.z); v.w = fmaf(v.w, s.w, t.w);
-            }
+            if (scale) { v.x = fmaf(v.x, c.s.x, c.t.x); v.y = fmaf(v.y, c.s.y, c.t.y); v.z = fmaf(v.z, c.s.z, c.t.z); v.w = fmaf(v.w, c.s.w, c.t.w); }
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         }
         return v;
     }
+    __device__ __forceinline__ float4 load(int p, int P, int k, int K) const { return row(prep(k, K), p, P, k); }
 };
 
 struct TcDy {
     const float* g; int ldg; const float* y; int ldy; const float* a; const float* b; const float* cc;
     const float* dpool; const int32_t* sel; int S; int ldp;
-    __device__ __forceinline__ float4 load(int p, int P, int c, int C) const {
+    struct Coef { float4 a, b, c; bool on; };
+    __device__ __forceinline__ Coef prep(int k, int K) const {
+        Coef c;
+        c.on = k < K;
+        c.a = make_float4(1.f, 1.f, 1.f, 1.f);
+        c.b = c.c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c.on && a) { c.a = ld4g(a + k); c.b = ld4g(b + k); c.c = ld4g(cc + k); }
+        return c;
+    }
+    __device__ __forceinline__ float4 row(const Coef& c, int p, int P, int k) const {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < P && c < C) {
+        if (c.on && p < P) {
             if (dpool) {
                 const int grp = p / S, s = p - grp * S;
-                const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + (size_t)grp * ldp + c));
-                const float4 d = ld4g(dpool + (size_t)grp * ldp + c);
+                const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + (size_t)grp * ldp + k));
+                const float4 d = ld4g(dpool + (size_t)grp * ldp + k);
                 v.x = sl.x == s ? d.x : 0.f; v.y = sl.y == s ? d.y : 0.f; v.z = sl.z == s ? d.z : 0.f; v.w = sl.w == s ? d.w : 0.f;
             } else {
-                v = ld4g(g + (size_t)p * ldg + c);
+                v = ld4g(g + (size_t)p * ldg + k);
             }
             if (a) {
-                const float4 aa = ld4g(a + c), bb = ld4g(b + c), c2 = ld4g(cc + c);
-                const float4 yy = ld4g(y + (size_t)p * ldy + c);
-                v.x = fmaf(aa.x, v.x, fmaf(c2.x, yy.x, bb.x)); v.y = fmaf(aa.y, v.y, fmaf(c2.y, yy.y, bb.y));
-                v.z = fmaf(aa.z, v.z, fmaf(c2.z, yy.z, bb.z)); v.w = fmaf(aa.w, v.w, fmaf(c2.w, yy.w, bb.w));
+                const float4 yy = ld4g(y + (size_t)p * ldy + k);
+                v.x = fmaf(c.a.x, v.x, fmaf(c.c.x, yy.x, c.b.x)); v.y = fmaf(c.a.y, v.y, fmaf(c.c.y, yy.y, c.b.y));
+                v.z = fmaf(c.a.z, v.z, fmaf(c.c.z, yy.z, c.b.z)); v.w = fmaf(c.a.w, v.w, fmaf(c.c.w, yy.w, c.b.w));
             }
         }
         return v;
     }
+    __device__ __forceinline__ float4 load(int p, int P, int k, int K) const { return row(prep(k, K), p, P, k); }
 };
 
 // ---- epilogues: thread = one output channel `ch`, called once per 32-position column group ------------------
 struct TcFwdEpi {
     float* y; int ldy; const float* bias; double* sum; double* sumsq;
-    int S; float* ymax; float* ymin; int32_t* arg; int ldp;
+    int S, log2S; float* ymax; float* ymin; int32_t* arg; int ldp;
     // per-thread running state (fp32 inside a 32-position group, fp64 across groups and tiles)
     float bv, mx, mn; int ax, an; double d1, d2;
     __device__ __forceinline__ void begin(int ch, int Nw) {
@@ -159,24 +174,26 @@ struct TcFwdEpi {
         bv = (bias && ch < Nw) ? bias[ch] : 0.f;
         mx = -INFINITY; mn = INFINITY; ax = an = 0;
     }
+    __device__ __forceinline__ void prefetch(int, int, int, int) {}
     __device__ __forceinline__ void group(const uint32_t (&r)[32], int ch, int Nw, int pbase, int P) {
         if (ch >= Nw) return;
         float s1 = 0.f, s2 = 0.f;
+        const int smask = S - 1;
+        float* yp = y ? y + (size_t)pbase * ldy + ch : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const int p = pbase + j;
-            if (p >= P) break;
+            if (pbase + j >= P) break;
             const float v = __uint_as_float(r[j]) + bv;
-            if (y) y[(size_t)p * ldy + ch] = v;
+            if (yp) yp[(size_t)j * ldy] = v;
             s1 += v;
             s2 = fmaf(v, v, s2);
             if (S > 0) {
-                const int s = p % S;
+                const int s = (pbase + j) & smask;
                 if (s == 0) { mx = -INFINITY; mn = INFINITY; ax = an = 0; }
                 if (v > mx) { mx = v; ax = s; }
                 if (v < mn) { mn = v; an = s; }
-                if (s == S - 1) {
-                    const size_t o = (size_t)(p / S) * ldp + ch;
+                if (s == smask) {
+                    const size_t o = (size_t)((pbase + j) >> log2S) * ldp + ch;
                     ymax[o] = mx; ymin[o] = mn; arg[o] = ax | (an << 16);
                 }
             }
@@ -196,26 +213,32 @@ struct TcDgradEpi {
     float* out; int ldo; const float* yprev; int ldyp; const float* scale; const float* shift; int relu;
     double* s1g; double* s2y;
     float sc, sh; double d1, d2;
+    float yv[32];
     __device__ __forceinline__ void begin(int ch, int Nw) {
         d1 = d2 = 0.0;
         sc = (scale && ch < Nw) ? scale[ch] : 1.f;
         sh = (shift && ch < Nw) ? shift[ch] : 0.f;
     }
+    // issue the previous layer's raw outputs for this column group before waiting on TMEM (independent loads)
+    __device__ __forceinline__ void prefetch(int ch, int Nw, int pbase, int P) {
+        if (!yprev || ch >= Nw) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) yv[j] = (pbase + j < P) ? __ldg(yprev + (size_t)(pbase + j) * ldyp + ch) : 0.f;
+    }
     __device__ __forceinline__ void group(const uint32_t (&r)[32], int ch, int Nw, int pbase, int P) {
         if (ch >= Nw) return;
         float s1 = 0.f, s2 = 0.f;
+        float* op = out + (size_t)pbase * ldo + ch;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const int p = pbase + j;
-            if (p >= P) break;
+            if (pbase + j >= P) break;
             float v = __uint_as_float(r[j]);
             if (yprev) {
-                const float yv = __ldg(yprev + (size_t)p * ldyp + ch);
-                if (relu && !(fmaf(yv, sc, sh) > 0.f)) v = 0.f;
-                s2 = fmaf(v, yv, s2);
+                if (relu && !(fmaf(yv[j], sc, sh) > 0.f)) v = 0.f;
+                s2 = fmaf(v, yv[j], s2);
             }
             s1 += v;
-            out[(size_t)p * ldo + ch] = v;
+            op[(size_t)j * ldo] = v;
         }
         d1 += (double)s1;
         d2 += (double)s2;
@@ -229,34 +252,48 @@ struct TcDgradEpi {
 };
 
 // ------------------------------------------------------------------------------------------------------------
-template <class BLoad, class Epi>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// MT = number of 128-channel tiles one CTA accumulates for the same 128 positions (1 or 2).  With MT = 2 the
+// activation tile is produced once for 256 output channels: producer and epilogue work per MMA halve.
+//   warps: 0 MMA issuer (+TMEM alloc) | 1 weight streamer | 4-7, 8-11 epilogue | 12-15 producers        (512 threads)
+//   MT=2: epilogue warps 4-7 own channel tile 0, warps 8-11 tile 1 (all 128 columns each)
+//   MT=1: warps 4-7 take columns 0-63, warps 8-11 columns 64-127 of the single tile
+template <int MT> struct TcCfg {
+    static constexpr int STAGES = MT == 2 ? 2 : 3;
+    static constexpr int STAGE_BYTES_ = (2 * MT + 2) * TILE_BYTES;      // MT x (Whi|Wlo) | Xhi | Xlo
+    static constexpr int SMEM = STAGES * STAGE_BYTES_ + 1024 + 256;
+    static constexpr uint32_t TMEM = MT == 2 ? 512 : 256;
+};
+constexpr int TC2_THREADS = 512;
+
+template <int MT, class BLoad, class Epi>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
     pw_tc_kernel(BLoad bl, const uint8_t* __restrict__ wtiles, int P, int K, int Nw, int nkb, Epi epi) {
+    using C = TcCfg<MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                      // [TC_STAGES]  producers + weight copy -> MMA
-    uint64_t* empty = bars + TC_STAGES;         // [TC_STAGES]  MMA (tcgen05.commit) -> producers
-    uint64_t* tfull = bars + 2 * TC_STAGES;     // [2]          MMA -> epilogue
-    uint64_t* tempty = bars + 2 * TC_STAGES + 2;  // [2]        epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES_);
+    uint64_t* full = bars;                        // [STAGES]  producers + weight copy -> MMA
+    uint64_t* empty = bars + C::STAGES;           // [STAGES]  MMA (tcgen05.commit) -> producers
+    uint64_t* tfull = bars + 2 * C::STAGES;       // [2]       MMA -> epilogue
+    uint64_t* tempty = bars + 2 * C::STAGES + 2;  // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.y;
+    const int mt0 = blockIdx.y * MT;              // first 128-channel tile of this CTA
     const int n_ptiles = (P + TC_N - 1) / TC_N;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < C::STAGES; ++s) {
             o3d_mbar_init(full + s, 128 + 1);
             o3d_mbar_init(empty + s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             o3d_mbar_init(tfull + a, 1);
-            o3d_mbar_init(tempty + a, 128);
+            o3d_mbar_init(tempty + a, 256);
         }
         o3d_fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 0) tmem_alloc(tmem_slot, C::TMEM);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -269,26 +306,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
             o3d_mbar_wait(tempty + acc, aphase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
             for (int kb = 0; kb < nkb; ++kb) {
                 o3d_mbar_wait(full + stage, phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t sb = o3d_smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t whi = make_desc(sb), wlo = make_desc(sb + TILE_BYTES);
-                    const uint64_t xhi = make_desc(sb + 2 * TILE_BYTES), xlo = make_desc(sb + 3 * TILE_BYTES);
+                    const uint32_t sb = o3d_smem_u32(smem + stage * C::STAGE_BYTES_);
+                    const uint64_t xhi = make_desc(sb + 2 * MT * TILE_BYTES), xlo = make_desc(sb + (2 * MT + 1) * TILE_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < TC_K / 8; ++ks) {
-                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // +32 bytes along K inside the 128B swizzle row
-                        umma_tf32(d_tmem, wlo + adv, xhi + adv, idesc, (kb | ks) != 0);
-                        umma_tf32(d_tmem, whi + adv, xlo + adv, idesc, 1u);
-                        umma_tf32(d_tmem, whi + adv, xhi + adv, idesc, 1u);
+                    for (int m = 0; m < MT; ++m) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + m) * TC_N);
+                        const uint64_t whi = make_desc(sb + 2 * m * TILE_BYTES), wlo = make_desc(sb + (2 * m + 1) * TILE_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < TC_K / 8; ++ks) {
+                            const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // +32 bytes along K inside the 128B swizzle row
+                            umma_tf32(d_tmem, wlo + adv, xhi + adv, idesc, (kb | ks) != 0);
+                            umma_tf32(d_tmem, whi + adv, xlo + adv, idesc, 1u);
+                            umma_tf32(d_tmem, whi + adv, xhi + adv, idesc, 1u);
+                        }
                     }
                     umma_commit(empty + stage);                           // frees the stage when these MMAs retire
-                    if (kb == nkb - 1) umma_commit(tfull + acc);          // accumulator complete -> epilogue
+                    if (kb == nkb - 1) umma_commit(tfull + acc);          // accumulators complete -> epilogue
                 }
                 __syncwarp();
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
@@ -299,54 +339,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     o3d_mbar_wait(empty + stage, phase ^ 1);
-                    o3d_mbar_expect_tx(full + stage, 2 * TILE_BYTES);
-                    o3d_bulk_g2s(smem + stage * STAGE_BYTES, wtiles + ((size_t)m_tile * nkb + kb) * (2 * TILE_BYTES),
-                                 2 * TILE_BYTES, full + stage);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    o3d_mbar_expect_tx(full + stage, MT * 2 * TILE_BYTES);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        o3d_bulk_g2s(smem + stage * C::STAGE_BYTES_ + 2 * m * TILE_BYTES,
+                                     wtiles + ((size_t)(mt0 + m) * nkb + kb) * (2 * TILE_BYTES), 2 * TILE_BYTES, full + stage);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================================================== epilogue
+    } else if (warp >= 4 && warp < 12) {
+        // ===================================================== epilogue (8 warps)
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int ch = m_tile * TC_M + q * 32 + lane;
+        const int grp = (warp - 4) >> 2;              // 0: warps 4-7, 1: warps 8-11
+        const int m = MT == 2 ? grp : 0;              // channel tile inside the CTA
+        const int cg0 = MT == 2 ? 0 : grp * 2, cg1 = MT == 2 ? 4 : grp * 2 + 2;   // 32-column groups to handle
+        const int ch = (mt0 + m) * TC_M + q * 32 + lane;
         epi.begin(ch, Nw);
         int acc = 0, aphase = 0;
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
+            epi.prefetch(ch, Nw, t * TC_N + cg0 * 32, P);
             o3d_mbar_wait(tfull + acc, aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + m) * TC_N);
 #pragma unroll 1
-            for (int cg = 0; cg < TC_N / 32; ++cg) {
+            for (int cg = cg0; cg < cg1; ++cg) {
                 uint32_t r[32];
                 tmem_ld32(taddr + cg * 32, r);
                 epi.group(r, ch, Nw, t * TC_N + cg * 32, P);
+                if (cg + 1 < cg1) epi.prefetch(ch, Nw, t * TC_N + (cg + 1) * 32, P);
             }
             tc_fence_before();
             o3d_mbar_arrive(tempty + acc);
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         epi.end(ch, Nw);
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // ===================================================== activation-operand producers (128 threads)
-        const int pt = threadIdx.x - 256;             // 0..127
+        const int pt = threadIdx.x - 384;             // 0..127
         const int chunk = pt & 7;                     // 16-byte chunk (4 channels) inside the 128-byte row
         const int row0 = pt >> 3;                     // rows row0 + 16*i
         int stage = 0, phase = 0;
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
             const int p0 = t * TC_N;
             float4 v[8];
+            {
+                const auto c = bl.prep(chunk * 4, K);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = bl.load(p0 + row0 + 16 * i, P, chunk * 4, K);
+                for (int i = 0; i < 8; ++i) v[i] = bl.row(c, p0 + row0 + 16 * i, P, chunk * 4);
+            }
             for (int kb = 0; kb < nkb; ++kb) {
                 float4 nx[8];
                 const bool more = kb + 1 < nkb;
                 if (more) {
+                    const int k = (kb + 1) * TC_K + chunk * 4;
+                    const auto c = bl.prep(k, K);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) nx[i] = bl.load(p0 + row0 + 16 * i, P, (kb + 1) * TC_K + chunk * 4, K);
+                    for (int i = 0; i < 8; ++i) nx[i] = bl.row(c, p0 + row0 + 16 * i, P, k);
                 }
                 o3d_mbar_wait(empty + stage, phase ^ 1);
-                uint8_t* xhi = smem + stage * STAGE_BYTES + 2 * TILE_BYTES;
+                uint8_t* xhi = smem + stage * C::STAGE_BYTES_ + 2 * MT * TILE_BYTES;
                 uint8_t* xlo = xhi + TILE_BYTES;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -360,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = nx[i];
                 }
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     }
@@ -368,7 +420,154 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, C::TMEM);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad on the tensor core:  dW[m, n] += sum_p dY[p, m] * X[p, n]  over this CTA's slice of positions.
+// Both operands are position-major in global memory (channels contiguous), i.e. "MN-major" for a GEMM whose K is the
+// position index.  They are written to shared memory in the MN-major SWIZZLE_128B canonical layout — atoms of
+// 8 positions x 32 channels (1 KB), 16-byte chunk index XOR (position % 8) — so the producers copy coalesced float4
+// rows without any transposition; the instruction descriptor marks A and B as MN-major.
+//   tile [32 positions x 128 channels]:  atom(cb, pb) at (cb + 4*pb) * 1024,  cb = channel/32, pb = position/8
+//   descriptor for k-step pb: start = tile + pb*4096, LBO = 1024 (next 32-channel block), SBO = 4096 (next 8 positions)
+constexpr int WG_THREADS = 512;
+constexpr int WG_SMEM = TC_STAGES * STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 16;   // leading byte offset: between 32-channel blocks
+    d |= (uint64_t)(4096 >> 4) << 32;   // stride byte offset : between 8-position blocks
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+    return make_idesc(M, N) | (1u << 15) | (1u << 16);
+}
+__device__ __forceinline__ uint32_t sw128_mn(int p_local, int c4) {   // c4 = float4 index along the 128 channels
+    return (uint32_t)(((c4 >> 3) + 4 * (p_local >> 3)) * 1024 + (p_local & 7) * 128 + (((c4 & 7) ^ (p_local & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+    pw_wgrad_tc_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ dW, int lddw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + TC_STAGES;
+    uint64_t* tfull = bars + 2 * TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.z * TC_M, n0 = blockIdx.y * TC_N;
+    const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
+    const int nkb = (pend - pbeg + TC_K - 1) / TC_K;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            o3d_mbar_init(full + s, 256);
+            o3d_mbar_init(empty + s, 1);
+        }
+        o3d_mbar_init(tfull, 1);
+        o3d_fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        const uint32_t idesc = make_idesc_mn(TC_M, TC_N);
+        int stage = 0, phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            o3d_mbar_wait(full + stage, phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sb = o3d_smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+                for (int pb = 0; pb < TC_K / 8; ++pb) {
+                    const uint32_t o = pb * 4096;
+                    const uint64_t ahi = make_desc_mn(sb + o), alo = make_desc_mn(sb + TILE_BYTES + o);
+                    const uint64_t bhi = make_desc_mn(sb + 2 * TILE_BYTES + o), blo = make_desc_mn(sb + 3 * TILE_BYTES + o);
+                    umma_tf32(tmem_base, alo, bhi, idesc, (kb | pb) != 0);
+                    umma_tf32(tmem_base, ahi, blo, idesc, 1u);
+                    umma_tf32(tmem_base, ahi, bhi, idesc, 1u);
+                }
+                umma_commit(empty + stage);
+                if (kb == nkb - 1) umma_commit(tfull);
+            }
+            __syncwarp();
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        if (nkb > 0) {
+            const int q = warp & 3;
+            const int ch = m0 + q * 32 + lane;
+            o3d_mbar_wait(tfull, 0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int cg = 0; cg < TC_N / 32; ++cg) {
+                uint32_t r[32];
+                tmem_ld32(taddr + cg * 32, r);
+                if (ch < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + cg * 32 + j;
+                        if (n < N) atomicAdd(dW + (size_t)ch * lddw + n, __uint_as_float(r[j]));
+                    }
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // producers: warps 8-11 -> A (dY, channels m0..), warps 12-15 -> B (X, channels n0..)
+        const bool isA = warp < 12;
+        const int pt = (threadIdx.x - 256) & 127;
+        const int c4 = pt & 31, prow0 = pt >> 5;      // rows prow0 + 4*i
+        int stage = 0, phase = 0;
+        float4 v[8];
+        auto ldrow = [&](int kb, int i) {
+            const int p = pbeg + kb * TC_K + prow0 + 4 * i;
+            return isA ? da.load(p, pend, m0 + c4 * 4, M) : xb.load(p, pend, n0 + c4 * 4, N);
+        };
+        if (nkb > 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ldrow(0, i);
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+            float4 nx[8];
+            const bool more = kb + 1 < nkb;
+            if (more) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nx[i] = ldrow(kb + 1, i);
+            }
+            o3d_mbar_wait(empty + stage, phase ^ 1);
+            uint8_t* hi = smem + stage * STAGE_BYTES + (isA ? 0 : 2 * TILE_BYTES);
+            uint8_t* lo = hi + TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t off = sw128_mn(prow0 + 4 * i, c4);
+                *reinterpret_cast<float4*>(hi + off) = hi_part(v[i]);
+                *reinterpret_cast<float4*>(lo + off) = lo_part(v[i]);
+            }
+            o3d_fence_proxy_async();
+            o3d_mbar_arrive(full + stage);
+            if (more) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = nx[i];
+            }
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
     }
 }
 
@@ -388,19 +587,28 @@ __global__ void w_pretile_kernel(const float* __restrict__ W, int ld, int rows, 
     }
 }
 
-template <class BLoad, class Epi>
-int launch_tc(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cudaStream_t st, const char* name) {
-    auto kern = pw_tc_kernel<BLoad, Epi>;
-    O3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), name);
+template <int MT, class BLoad, class Epi>
+int launch_tc_mt(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cudaStream_t st, const char* name) {
+    auto kern = pw_tc_kernel<MT, BLoad, Epi>;
+    O3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MT>::SMEM), name);
     const int mt = (Nw + TC_M - 1) / TC_M;
+    const int gy = (mt + MT - 1) / MT;
     const int nkb = (K + TC_K - 1) / TC_K;
     const int n_ptiles = (P + TC_N - 1) / TC_N;
-    int gx = o3d_num_sms() / mt;
+    int gx = o3d_num_sms() / gy;
     if (gx < 1) gx = 1;
     if (gx > n_ptiles) gx = n_ptiles;
-    kern<<<dim3(gx, mt), TC_THREADS, TC_SMEM, st>>>(bl, wtiles, P, K, Nw, nkb, epi);
+    kern<<<dim3(gx, gy), TC2_THREADS, TcCfg<MT>::SMEM, st>>>(bl, wtiles, P, K, Nw, nkb, epi);
     O3D_CHECK_LAUNCH(name);
     return O3D_OK;
+}
+
+// Nw must be a multiple of 128 when more than one channel tile exists with MT = 2 (weight tiles are read pairwise).
+template <class BLoad, class Epi>
+int launch_tc(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cudaStream_t st, const char* name) {
+    const int mt = (Nw + TC_M - 1) / TC_M;
+    if (mt % 2 == 0) return launch_tc_mt<2>(bl, wtiles, P, K, Nw, epi, st, name);
+    return launch_tc_mt<1>(bl, wtiles, P, K, Nw, epi, st, name);
 }
 
 }  // namespace
@@ -425,13 +633,16 @@ extern "C" int o3d_pw_fwd_tc(const float* x, int ldx, const float* in_scale, con
                              double* sumsq, int S, float* ymax, float* ymin, int32_t* arg, int ldp, void* stream) {
     O3D_REQUIRE(x && wtiles, O3D_ERR_ARG, "o3d_pw_fwd_tc: null pointer");
     O3D_REQUIRE(P >= 0 && K >= 4 && N >= 1 && (K & 3) == 0 && (ldx & 3) == 0, O3D_ERR_ARG, "o3d_pw_fwd_tc: bad sizes");
-    O3D_REQUIRE(S == 0 || (P % S == 0 && ymax && ymin && arg), O3D_ERR_ARG, "o3d_pw_fwd_tc: bad pooling arguments");
+    O3D_REQUIRE(S == 0 || (P % S == 0 && 64 % S == 0 && ymax && ymin && arg), O3D_ERR_ARG,
+                "o3d_pw_fwd_tc: pooling group size must divide 64 and P");
     if (P == 0) return O3D_OK;
     const int Nw = (N + 3) & ~3;
     TcAct bl{x, ldx, in_scale, in_shift, in_relu};
     TcFwdEpi ep{};
     ep.y = y; ep.ldy = ldy; ep.bias = bias; ep.sum = sum; ep.sumsq = sumsq;
     ep.S = S; ep.ymax = ymax; ep.ymin = ymin; ep.arg = arg; ep.ldp = ldp;
+    ep.log2S = 0;
+    while ((1 << ep.log2S) < S) ++ep.log2S;
     return launch_tc(bl, (const uint8_t*)wtiles, P, K, Nw, ep, (cudaStream_t)stream, "o3d_pw_fwd_tc");
 }
 
@@ -449,4 +660,26 @@ extern "C" int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy,
     ep.s1g = s1; ep.s2y = s2y;
     // GEMM: D[cin, pos] = sum_cout Wt[cin, cout] * dY[pos, cout]  ->  "K" = Cout, "Nw" = Cin
     return launch_tc(bl, (const uint8_t*)wtiles_t, P, Cout, Cin, ep, (cudaStream_t)stream, "o3d_pw_dgrad_tc");
+}
+
+extern "C" int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
+                               const float* cc, const float* dpool, const int32_t* sel, int S, int ldp, const float* x,
+                               int ldx, const float* in_scale, const float* in_shift, int in_relu, int P, int Cout,
+                               int Cin, float* dw, int lddw, void* stream) {
+    O3D_REQUIRE((g || dpool) && x && dw, O3D_ERR_ARG, "o3d_pw_wgrad_tc: null pointer");
+    O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0 && (ldx & 3) == 0, O3D_ERR_ARG,
+                "o3d_pw_wgrad_tc: channel counts / leading dimensions must be multiples of 4");
+    if (P == 0) return O3D_OK;
+    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp};
+    TcAct xb{x, ldx, in_scale, in_shift, in_relu};
+    O3D_CUDA(cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "o3d_pw_wgrad_tc");
+    const int mt = (Cout + TC_M - 1) / TC_M, nt = (Cin + TC_N - 1) / TC_N;
+    int splits = o3d_num_sms() / (mt * nt);
+    if (splits < 1) splits = 1;
+    int chunk = (P + splits - 1) / splits;
+    chunk = ((chunk + TC_K - 1) / TC_K) * TC_K;
+    splits = (P + chunk - 1) / chunk;
+    pw_wgrad_tc_kernel<<<dim3(splits, nt, mt), WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(da, xb, P, Cout, Cin, chunk, dw, lddw);
+    O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc");
+    return O3D_OK;
 }

@@ -85,8 +85,9 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     for (int l = 0; l < p.n; ++l) {
         p.Nw[l] = r4(d->cout[l]);
         p.K[l] = l == 0 ? d->K0 : p.Nw[l - 1];
-        p.tc_f[l] = d->use_tc && p.Nw[l] >= 128 && p.K[l] >= 32 && d->P >= 128;
-        p.tc_b[l] = d->use_tc && p.K[l] >= 128 && p.Nw[l] >= 32 && d->P >= 128;
+        p.tc_f[l] = (d->use_tc & 1) && p.Nw[l] >= 128 && p.Nw[l] % 128 == 0 && p.K[l] >= 32 && d->P >= 128 &&
+                    !(l == d->n_layers - 1 && d->S > 0 && 64 % d->S != 0);
+        p.tc_b[l] = (d->use_tc & 1) && p.K[l] >= 128 && p.Nw[l] >= 32 && d->P >= 128;
     }
     // statistics block first (one memset)
     p.stat_all = o;
@@ -116,7 +117,7 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     for (int l = 0; l < p.n; ++l) {
         p.coef[l] = o; o += al(sizeof(float) * 5 * p.Nw[l]);
         p.dwp[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]);
-        p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(p.K[l], p.Nw[l]));
+        p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes((p.K[l] / 128) * 128, p.Nw[l]));
         if ((size_t)p.K[l] > maxk) maxk = p.K[l];
     }
     size_t maxn = 0;
@@ -285,7 +286,20 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         if (d->d_weight[l]) {
             float* dwp = at<float>(wb, p.dwp[l]);
             O3D_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)Nl * K, st), "o3d_stack_backward: memset dW");
-            rc = o3d_pw_wgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, K, dwp, K, stream);
+            const bool tcw = (d->use_tc & 2) && Nl >= 128 && K >= 128 && p.P >= 4096;
+            if (tcw) {
+                // tensor-core part: the first floor(K/128)*128 input channels; ragged tail (xyz / box-cloud extras)
+                // goes through the exact CUDA-core kernel on the remaining columns
+                const int Kmain = (K / 128) * 128;
+                rc = o3d_pw_wgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, Kmain, dwp, K,
+                                     stream);
+                if (rc) return rc;
+                if (K > Kmain)
+                    rc = o3d_pw_wgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin + Kmain, K, psc ? psc + Kmain : nullptr,
+                                      psh ? psh + Kmain : nullptr, prelu, p.P, Nl, K - Kmain, dwp + Kmain, K, stream);
+            } else {
+                rc = o3d_pw_wgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, K, dwp, K, stream);
+            }
             if (rc) return rc;
             unpack_wgrad_kernel<<<(cout * K + 255) / 256, 256, 0, st>>>(dwp, cout, d->cin[l], K, l == 0 ? d->xyz_first : 0,
                                                                         d->c0, d->d_weight[l]);
@@ -299,11 +313,19 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
             double* ps1 = want ? s1(l - 1) : nullptr;
             double* ps2 = want ? s1(l - 1) + K : nullptr;
             if (p.tc_b[l]) {
+                // tensor cores on the first floor(K/128)*128 input channels, exact CUDA-core kernel on the ragged tail
+                // (the xyz / box-cloud extras of a first layer)
+                const int Km = (K / 128) * 128;
                 void* tiles = wb + p.btiles[l];
-                rc = o3d_pw_tc_pretile(at<float>(wf, p.wt[l]), Nl, K, Nl, tiles, stream);
+                rc = o3d_pw_tc_pretile(at<float>(wf, p.wt[l]), Nl, Km, Nl, tiles, stream);
                 if (rc) return rc;
-                rc = o3d_pw_dgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, tiles, p.P, Nl, K, gout, K, yprev, K, psc, psh,
+                rc = o3d_pw_dgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, tiles, p.P, Nl, Km, gout, K, yprev, K, psc, psh,
                                      prelu, ps1, ps2, stream);
+                if (rc) return rc;
+                if (K > Km)
+                    rc = o3d_pw_dgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, at<float>(wf, p.wp[l]) + Km, K, p.P, Nl, K - Km,
+                                      gout + Km, K, yprev ? yprev + Km : nullptr, K, psc ? psc + Km : nullptr,
+                                      psh ? psh + Km : nullptr, prelu, ps1 ? ps1 + Km : nullptr, ps2 ? ps2 + Km : nullptr, stream);
             } else {
                 rc = o3d_pw_dgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, at<float>(wf, p.wp[l]), K, p.P, Nl, K, gout, K,
                                   yprev, K, psc, psh, prelu, ps1, ps2, stream);

@@ -1,0 +1,78 @@
+"""Training-step engine: flat parameter bucket + one-launch Adam + optional whole-step CUDA graph.
+
+The reference trains through Lightning (`main.py:82-86`): per step DDP-wrapped `training_step`, backward, bucketed
+all-reduce, `Adam(betas=(0.5, 0.999), eps=1e-6)` (`models/base_model.py:28-36`).  A BAT step is a few milliseconds of GPU
+work spread over ~10^3 kernel launches, so the step is launch-bound unless it is captured: `TrainStep` records
+zero-grad -> training_step -> backward -> gradient all-reduce -> Adam into ONE CUDA graph over static batch buffers
+and replays it; the loss stays on the device (the reference's twelve `.item()` syncs per step, `bat.py:146-163`, are
+not reproduced).
+"""
+import torch
+
+from . import _lib, ddp, ops
+
+
+class FlatAdam:
+    """Adam over `FlatParams` with the step counter and learning rate in device memory (graph-replayable)."""
+
+    def __init__(self, flat, lr=1e-3, betas=(0.5, 0.999), eps=1e-6, weight_decay=0.0):
+        self.flat = flat
+        self.betas, self.eps, self.wd = betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_avg_sq = torch.zeros_like(flat.flat)
+        self.state = torch.tensor([0.0, lr], dtype=torch.float32, device=flat.flat.device)
+
+    def set_lr(self, lr):
+        self.state[1] = lr
+
+    def step(self):
+        ops._call("o3d_adam_step", self.flat.flat.data_ptr(), self.flat.grad.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), self.flat.numel, self.state.data_ptr(), self.betas[0], self.betas[1],
+                  self.eps, self.wd, ops._stream())
+
+
+class TrainStep:
+    """`step(batch) -> loss` for a model exposing `training_step(batch, idx)`; `batch` is a dict of device tensors."""
+
+    def __init__(self, model, lr=1e-3, weight_decay=0.0, use_graph=True, warmup=3):
+        self.model = model
+        self.flat = ddp.FlatParams(model)
+        ddp.broadcast_parameters(self.flat, model)
+        self.opt = FlatAdam(self.flat, lr=lr, weight_decay=weight_decay)
+        self.use_graph = use_graph
+        self.warmup = warmup
+        self.graph = None
+        self.static_batch = None
+        self.static_loss = None
+        self.calls = 0
+
+    def _eager(self, batch):
+        self.flat.zero_grad()
+        loss = self.model.training_step(dict(batch), 0)
+        loss.backward()
+        ddp.allreduce_gradients(self.flat)
+        self.opt.step()
+        return loss.detach()
+
+    def _capture(self, batch):
+        self.static_batch = {k: v.clone() for k, v in batch.items()}
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):                       # settle allocator / lazy initialisation on the capture stream
+                self._eager(self.static_batch)
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._eager(self.static_batch)
+
+    def step(self, batch):
+        self.calls += 1
+        if not self.use_graph or self.calls <= self.warmup:
+            return self._eager(batch)
+        if self.graph is None:
+            self._capture(batch)
+        for k, v in batch.items():
+            self.static_batch[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss

@@ -95,7 +95,7 @@ class _Meta:
 def _describe(meta, P, K0, params):
     d = _lib.StackDesc()
     d.n_layers, d.P, d.K0, d.S = meta.n, P, K0, meta.S
-    d.training, d.use_tc = int(meta.training), int(runtime.tc_enabled())
+    d.training, d.use_tc = int(meta.training), int(runtime.tc_level())
     d.xyz_first, d.c0 = int(meta.xyz_first), meta.c0
     for l in range(meta.n):
         W, b, g, be = params[4 * l:4 * l + 4]

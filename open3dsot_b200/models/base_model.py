@@ -52,7 +52,7 @@ class MatchingBaseModel(BaseModel):
         objectness_mask = ((dist < 0.3) | (dist > 0.6)).float()
         loss_objective = F.binary_cross_entropy_with_logits(
             estimation_boxes[:, :, 4], objectness_label, reduction='none',
-            pos_weight=torch.tensor([2.0], device=estimation_boxes.device))
+            pos_weight=torch.full((1,), 2.0, device=estimation_boxes.device))   # device-side fill: graph-capturable
         loss_objective = torch.sum(loss_objective * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
 
         loss_box = F.smooth_l1_loss(estimation_boxes[:, :, :4],

@@ -5,16 +5,21 @@ import os
 _FUSED = os.environ.get("O3D_FUSED", "1") != "0"
 
 
-_TC = os.environ.get("O3D_TC", "0") != "0"  # tcgen05 3xTF32 GEMM core for the point-wise layers
+# tcgen05 3xTF32 GEMM core for the point-wise layers: bit 0 = forward + dgrad, bit 1 = wgrad  (0 = exact-fp32 CUDA cores)
+_TC = int(os.environ.get("O3D_TC", "0"))
 
 
 def tc_enabled() -> bool:
+    return _TC != 0
+
+
+def tc_level() -> int:
     return _TC
 
 
-def set_tc(flag: bool) -> None:
+def set_tc(level) -> None:
     global _TC
-    _TC = bool(flag)
+    _TC = int(level)
 
 
 def fused_enabled() -> bool:

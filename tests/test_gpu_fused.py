@@ -1,6 +1,8 @@
 """The fused point-wise MLP kernels (csrc/pwmlp.cu through open3dsot_b200.fused.mlp_stack) against a plain
 fp64 PyTorch statement of the same stack (1x1 conv -> BatchNorm(train|eval) -> ReLU -> max over groups), forward
 and backward, including ragged P, Cout not a multiple of 4, negative BN gammas and every group size in use."""
+import zlib
+
 import pytest
 import torch
 import torch.nn as nn
@@ -70,7 +72,7 @@ CASES = [
 @pytest.mark.parametrize("name,chans,P,S,kind", CASES)
 @pytest.mark.parametrize("training", [True, False])
 def test_mlp_stack_matches_fp64_reference(name, chans, P, S, kind, training):
-    torch.manual_seed(hash(name) % 1000)
+    torch.manual_seed(zlib.crc32(name.encode()) % 1000)   # fixed per case (hash() is randomised per process)
     if kind == "shared":
         mod = pt.SharedMLP(list(chans), bn=True)
     else:
@@ -129,8 +131,9 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("name,chans,P,S", TC_CASES)
-def test_tensor_core_stack_matches_fp64_reference(name, chans, P, S):
+@pytest.mark.parametrize("level", [1, 3])
+@pytest.mark.parametrize("name,chans,P,S", TC_CASES + [("tc_wgrad_big", [260, 256, 256, 256], 32 * 160, 32)])
+def test_tensor_core_stack_matches_fp64_reference(name, chans, P, S, level):
     """tcgen05 3xTF32 forward + dgrad against the fp64 statement: same 1e-4 bar as the exact-fp32 kernels."""
     from open3dsot_b200 import runtime
     torch.manual_seed(3)
@@ -141,8 +144,8 @@ def test_tensor_core_stack_matches_fp64_reference(name, chans, P, S):
     x = torch.randn(P, chans[0], device="cuda")
     x[:, -1] = 0
     x1 = x.clone().requires_grad_(True)
-    old = runtime.tc_enabled()
-    runtime.set_tc(True)
+    old = runtime.tc_level()
+    runtime.set_tc(level)
     try:
         out = fused.mlp_stack(x1, specs, S, True)
         x2 = x.clone().requires_grad_(True)
