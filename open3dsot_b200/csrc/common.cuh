@@ -112,6 +112,22 @@ __device__ __forceinline__ void o3d_bulk_g2s(void* smem_dst, const void* gsrc, u
         "l"(gsrc), "r"(bytes), "r"(o3d_smem_u32(bar))
         : "memory");
 }
+// Ask the bulk-copy engine to pull a contiguous global range into L2 (no SM-side destination).  The activation
+// matrices are read in 64..128-byte column slices per k-block; without this every slice re-opens the DRAM page of
+// its row (row = 1 KB), with it DRAM streams each tile once, contiguously, and the slices hit L2.
+__device__ __forceinline__ void o3d_prefetch_l2(const void* gptr, size_t bytes) {
+    const char* p = static_cast<const char*>(gptr);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uintptr_t lo = a & ~(uintptr_t)15;
+    size_t n = ((a - lo) + bytes + 15) & ~(size_t)15;
+    const char* q = reinterpret_cast<const char*>(lo);
+    while (n > 0) {
+        const uint32_t c = n > (1u << 20) ? (1u << 20) : (uint32_t)n;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(c) : "memory");
+        q += c;
+        n -= c;
+    }
+}
 __device__ __forceinline__ uint32_t o3d_lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

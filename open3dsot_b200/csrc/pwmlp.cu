@@ -55,38 +55,60 @@ struct DyIn {  // dY[p, c] = a[c]*g[p,c] + b[c] + cc[c]*y[p,c]      (a == nullpt
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-__device__ __forceinline__ float4 load_act(const ActIn& in, int p, int P, int k, int K) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p < P && k < K) {
-        v = ld4(in.x + (size_t)p * in.ld + k);
-        if (in.scale) {
-            const float4 s = ld4(in.scale + k), t = ld4(in.shift + k);
-            v.x = fmaf(v.x, s.x, t.x); v.y = fmaf(v.y, s.y, t.y); v.z = fmaf(v.z, s.z, t.z); v.w = fmaf(v.w, s.w, t.w);
-        }
-        if (in.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+// Operand loads are split in two so that the register-prefetch double buffering really overlaps memory latency with the
+// FMA loop: fetch_*() issues only address-independent global loads (clamped, always in range) BEFORE the tile's math,
+// finish_*() applies the per-channel transform (and the range mask) AFTER it, right before the st.shared.
+struct ActRaw { float4 v; };
+struct DyRaw { float4 g, y; };
+
+__device__ __forceinline__ ActRaw fetch_act(const ActIn& in, int p, int P, int k, int K) {
+    ActRaw r;
+    r.v = ld4(in.x + (size_t)(p < P ? p : P - 1) * in.ld + (k < K ? k : 0));
+    return r;
+}
+__device__ __forceinline__ float4 finish_act(const ActIn& in, const ActRaw& r, int p, int P, int k, int K) {
+    if (!(p < P && k < K)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = r.v;
+    if (in.scale) {
+        const float4 s = ld4(in.scale + k), t = ld4(in.shift + k);
+        v.x = fmaf(v.x, s.x, t.x); v.y = fmaf(v.y, s.y, t.y); v.z = fmaf(v.z, s.z, t.z); v.w = fmaf(v.w, s.w, t.w);
+    }
+    if (in.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+}
+__device__ __forceinline__ DyRaw fetch_dy(const DyIn& in, int p, int P, int c, int C) {
+    DyRaw r;
+    const int pp = p < P ? p : P - 1, cc = c < C ? c : 0;
+    if (in.dpool) {
+        const int grp = pp / in.S, s = pp - grp * in.S;
+        const int4 sl = __ldg(reinterpret_cast<const int4*>(in.sel + (size_t)grp * in.ldp + cc));
+        const float4 d = ld4(in.dpool + (size_t)grp * in.ldp + cc);
+        r.g = make_float4(sl.x == s ? d.x : 0.f, sl.y == s ? d.y : 0.f, sl.z == s ? d.z : 0.f, sl.w == s ? d.w : 0.f);
+    } else {
+        r.g = ld4(in.g + (size_t)pp * in.ldg + cc);
+    }
+    r.y = in.a ? ld4(in.y + (size_t)pp * in.ldy + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+}
+__device__ __forceinline__ float4 finish_dy(const DyIn& in, const DyRaw& r, int p, int P, int c, int C) {
+    if (!(p < P && c < C)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = r.g;
+    if (in.a) {
+        const float4 a = ld4(in.a + c), b = ld4(in.b + c), cc = ld4(in.cc + c);
+        v.x = fmaf(a.x, v.x, fmaf(cc.x, r.y.x, b.x)); v.y = fmaf(a.y, v.y, fmaf(cc.y, r.y.y, b.y));
+        v.z = fmaf(a.z, v.z, fmaf(cc.z, r.y.z, b.z)); v.w = fmaf(a.w, v.w, fmaf(cc.w, r.y.w, b.w));
     }
     return v;
 }
 
-__device__ __forceinline__ float4 load_dy(const DyIn& in, int p, int P, int c, int C) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p < P && c < C) {
-        if (in.dpool) {
-            const int grp = p / in.S, s = p - grp * in.S;
-            const int4 sl = __ldg(reinterpret_cast<const int4*>(in.sel + (size_t)grp * in.ldp + c));
-            const float4 d = ld4(in.dpool + (size_t)grp * in.ldp + c);
-            v.x = sl.x == s ? d.x : 0.f; v.y = sl.y == s ? d.y : 0.f; v.z = sl.z == s ? d.z : 0.f; v.w = sl.w == s ? d.w : 0.f;
-        } else {
-            v = ld4(in.g + (size_t)p * in.ldg + c);
-        }
-        if (in.a) {
-            const float4 a = ld4(in.a + c), b = ld4(in.b + c), cc = ld4(in.cc + c);
-            const float4 y = ld4(in.y + (size_t)p * in.ldy + c);
-            v.x = fmaf(a.x, v.x, fmaf(cc.x, y.x, b.x)); v.y = fmaf(a.y, v.y, fmaf(cc.y, y.y, b.y));
-            v.z = fmaf(a.z, v.z, fmaf(cc.z, y.z, b.z)); v.w = fmaf(a.w, v.w, fmaf(cc.w, y.w, b.w));
-        }
-    }
-    return v;
+__device__ __forceinline__ void prefetch_act(const ActIn& in, int p0, int rows, int P) {
+    if (p0 < P) o3d_prefetch_l2(in.x + (size_t)p0 * in.ld, (size_t)min(rows, P - p0) * in.ld * sizeof(float));
+}
+__device__ __forceinline__ void prefetch_dy(const DyIn& in, int p0, int rows, int P) {
+    if (p0 >= P) return;
+    const size_t n = (size_t)min(rows, P - p0);
+    if (!in.dpool) o3d_prefetch_l2(in.g + (size_t)p0 * in.ldg, n * in.ldg * sizeof(float));
+    if (in.a) o3d_prefetch_l2(in.y + (size_t)p0 * in.ldy, n * in.ldy * sizeof(float));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -244,6 +266,7 @@ __global__ void __launch_bounds__(NT, 2)
     float* Bs = smem + 2 * BM * AS_LD;
     const int tid = threadIdx.x, tx = tid % C::TX, ty = tid / C::TX;
     const int p0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (tid == 0 && blockIdx.y == 0 && K > 32) prefetch_act(ain, p0, BM, P);   // whole rows -> L2 once, contiguously
 
     float acc[C::TM][8];
 #pragma unroll
@@ -252,33 +275,34 @@ __global__ void __launch_bounds__(NT, 2)
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
     // A tile: 128 rows x 16 k = 512 float4 -> 2 per thread: row = id/4, kv = (id%4)*4
-    float4 ra[2];
+    ActRaw ra[2];
     BLoad<BN> rb;
     const int nk = (K + BK - 1) / BK;
     auto load_tiles = [&](int kt) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             const int id = tid + v * NT;
-            ra[v] = load_act(ain, p0 + id / 4, P, kt * BK + (id % 4) * 4, K);
+            ra[v] = fetch_act(ain, p0 + id / 4, P, kt * BK + (id % 4) * 4, K);
         }
         rb.load(Wt, ldw, K, N, kt * BK, n0, tid);
     };
-    auto store_tiles = [&](int buf) {
+    auto store_tiles = [&](int buf, int kt) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             const int id = tid + v * NT;
-            *reinterpret_cast<float4*>(As + buf * BM * AS_LD + (id / 4) * AS_LD + (id % 4) * 4) = ra[v];
+            *reinterpret_cast<float4*>(As + buf * BM * AS_LD + (id / 4) * AS_LD + (id % 4) * 4) =
+                finish_act(ain, ra[v], p0 + id / 4, P, kt * BK + (id % 4) * 4, K);
         }
         rb.store(Bs + buf * BK * C::BS_LD, tid);
     };
     load_tiles(0);
-    store_tiles(0);
+    store_tiles(0, 0);
     __syncthreads();
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
         if (kt + 1 < nk) load_tiles(kt + 1);
         mma_tile_mk<BN>(As + buf * BM * AS_LD, Bs + buf * BK * C::BS_LD, ty, tx, acc);
-        if (kt + 1 < nk) store_tiles(buf ^ 1);
+        if (kt + 1 < nk) store_tiles(buf ^ 1, kt + 1);
         __syncthreads();
     }
 
@@ -346,38 +370,40 @@ __global__ void __launch_bounds__(NT, 2)
     float* Bs = smem + 2 * BM * AS_LD;
     const int tid = threadIdx.x, tx = tid % C::TX, ty = tid / C::TX;
     const int p0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (tid == 0 && blockIdx.y == 0 && K > 32) prefetch_dy(din, p0, BM, P);
     float acc[C::TM][8];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    float4 ra[2];
+    DyRaw ra[2];
     BLoad<BN> rb;
     const int nk = (K + BK - 1) / BK;
     auto load_tiles = [&](int kt) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             const int id = tid + v * NT;
-            ra[v] = load_dy(din, p0 + id / 4, P, kt * BK + (id % 4) * 4, K);
+            ra[v] = fetch_dy(din, p0 + id / 4, P, kt * BK + (id % 4) * 4, K);
         }
         rb.load(W, ldw, K, N, kt * BK, n0, tid);
     };
-    auto store_tiles = [&](int buf) {
+    auto store_tiles = [&](int buf, int kt) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             const int id = tid + v * NT;
-            *reinterpret_cast<float4*>(As + buf * BM * AS_LD + (id / 4) * AS_LD + (id % 4) * 4) = ra[v];
+            *reinterpret_cast<float4*>(As + buf * BM * AS_LD + (id / 4) * AS_LD + (id % 4) * 4) =
+                finish_dy(din, ra[v], p0 + id / 4, P, kt * BK + (id % 4) * 4, K);
         }
         rb.store(Bs + buf * BK * C::BS_LD, tid);
     };
     load_tiles(0);
-    store_tiles(0);
+    store_tiles(0, 0);
     __syncthreads();
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
         if (kt + 1 < nk) load_tiles(kt + 1);
         mma_tile_mk<BN>(As + buf * BM * AS_LD, Bs + buf * BK * C::BS_LD, ty, tx, acc);
-        if (kt + 1 < nk) store_tiles(buf ^ 1);
+        if (kt + 1 < nk) store_tiles(buf ^ 1, kt + 1);
         __syncthreads();
     }
     float* Cs = smem;
@@ -421,6 +447,10 @@ __global__ void __launch_bounds__(NT, 2)
     const int tid = threadIdx.x, tx = tid % C::TX, ty = tid / C::TX;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int pbeg = blockIdx.z * chunk, pend = min(P, pbeg + chunk);
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {   // one CTA per position slice streams its rows into L2
+        prefetch_dy(din, pbeg, pend - pbeg, pend);
+        prefetch_act(ain, pbeg, pend - pbeg, pend);
+    }
     float acc[C::TM][8];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i)
@@ -428,43 +458,47 @@ __global__ void __launch_bounds__(NT, 2)
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     // A2 tile: 16 positions x 128 m = 512 float4 (2 / thread); B tile: 16 positions x BN (V / thread)
     constexpr int VB = BK * BN / 4 / NT;
-    float4 ra[2], rb[VB];
+    DyRaw ra[2];
+    ActRaw rb[VB];
     const int nk = (pend - pbeg + BK - 1) / BK;
     auto load_tiles = [&](int kt) {
         const int pk = pbeg + kt * BK;
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             const int id = tid + v * NT;
-            ra[v] = load_dy(din, pk + id / 32, pend, m0 + (id % 32) * 4, M);
+            ra[v] = fetch_dy(din, pk + id / 32, pend, m0 + (id % 32) * 4, M);
         }
 #pragma unroll
         for (int v = 0; v < VB; ++v) {
             const int id = tid + v * NT;
-            rb[v] = load_act(ain, pk + id / (BN / 4), pend, n0 + (id % (BN / 4)) * 4, N);
+            rb[v] = fetch_act(ain, pk + id / (BN / 4), pend, n0 + (id % (BN / 4)) * 4, N);
         }
     };
-    auto store_tiles = [&](int buf) {
+    auto store_tiles = [&](int buf, int kt) {
+        const int pk = pbeg + kt * BK;
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             const int id = tid + v * NT;
-            *reinterpret_cast<float4*>(A2 + buf * BK * C::A2_LD + (id / 32) * C::A2_LD + (id % 32) * 4) = ra[v];
+            *reinterpret_cast<float4*>(A2 + buf * BK * C::A2_LD + (id / 32) * C::A2_LD + (id % 32) * 4) =
+                finish_dy(din, ra[v], pk + id / 32, pend, m0 + (id % 32) * 4, M);
         }
 #pragma unroll
         for (int v = 0; v < VB; ++v) {
             const int id = tid + v * NT;
-            *reinterpret_cast<float4*>(Bs + buf * BK * C::BS_LD + (id / (BN / 4)) * C::BS_LD + (id % (BN / 4)) * 4) = rb[v];
+            *reinterpret_cast<float4*>(Bs + buf * BK * C::BS_LD + (id / (BN / 4)) * C::BS_LD + (id % (BN / 4)) * 4) =
+                finish_act(ain, rb[v], pk + id / (BN / 4), pend, n0 + (id % (BN / 4)) * 4, N);
         }
     };
     if (nk > 0) {
         load_tiles(0);
-        store_tiles(0);
+        store_tiles(0, 0);
     }
     __syncthreads();
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
         if (kt + 1 < nk) load_tiles(kt + 1);
         mma_tile_km<BN>(A2 + buf * BK * C::A2_LD, Bs + buf * BK * C::BS_LD, ty, tx, acc);
-        if (kt + 1 < nk) store_tiles(buf ^ 1);
+        if (kt + 1 < nk) store_tiles(buf ^ 1, kt + 1);
         __syncthreads();
     }
 #pragma unroll

@@ -73,6 +73,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 (ignored for
 // swizzled K-major) | SBO = 1024 B between 8-row groups | version 1 | layout 2 (SWIZZLE_128B).
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
@@ -109,6 +120,7 @@ __device__ __forceinline__ float4 ld4g(const float* p) { return __ldg(reinterpre
 struct TcAct {
     const float* x; int ld; const float* scale; const float* shift; int relu;
     struct Coef { float4 s, t; bool on; };
+    struct Raw { float4 v; };
     __device__ __forceinline__ Coef prep(int k, int K) const {
         Coef c;
         c.on = k < K;
@@ -117,22 +129,30 @@ struct TcAct {
         if (c.on && scale) { c.s = ld4g(scale + k); c.t = ld4g(shift + k); }
         return c;
     }
-    __device__ __forceinline__ float4 row(const Coef& c, int p, int P, int k) const {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c.on && p < P) {
-            v = ld4g(x + (size_t)p * ld + k);
-            if (scale) { v.x = fmaf(v.x, c.s.x, c.t.x); v.y = fmaf(v.y, c.s.y, c.t.y); v.z = fmaf(v.z, c.s.z, c.t.z); v.w = fmaf(v.w, c.s.w, c.t.w); }
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        }
+    // unconditional, always-in-range load (clamped indices): nothing here depends on loaded data, so a batch of
+    // fetches is issued back to back and all of them are in flight together; masking happens in finish()
+    __device__ __forceinline__ Raw fetch(int p, int P, int k, int K) const {
+        Raw r;
+        r.v = ld4g(x + (size_t)(p < P ? p : P - 1) * ld + (k < K ? k : 0));
+        return r;
+    }
+    __device__ __forceinline__ float4 finish(const Raw& r, const Coef& c, int p, int P) const {
+        float4 v = r.v;
+        if (!(c.on && p < P)) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale) { v.x = fmaf(v.x, c.s.x, c.t.x); v.y = fmaf(v.y, c.s.y, c.t.y); v.z = fmaf(v.z, c.s.z, c.t.z); v.w = fmaf(v.w, c.s.w, c.t.w); }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         return v;
     }
-    __device__ __forceinline__ float4 load(int p, int P, int k, int K) const { return row(prep(k, K), p, P, k); }
+    __device__ __forceinline__ void prefetch_rows(int p0, int rows, int P) const {   // full rows p0 .. p0+rows-1 -> L2
+        if (p0 < P) o3d_prefetch_l2(x + (size_t)p0 * ld, (size_t)min(rows, P - p0) * ld * sizeof(float));
+    }
 };
 
 struct TcDy {
     const float* g; int ldg; const float* y; int ldy; const float* a; const float* b; const float* cc;
     const float* dpool; const int32_t* sel; int S; int ldp;
     struct Coef { float4 a, b, c; bool on; };
+    struct Raw { float4 g, y; };
     __device__ __forceinline__ Coef prep(int k, int K) const {
         Coef c;
         c.on = k < K;
@@ -141,26 +161,35 @@ struct TcDy {
         if (c.on && a) { c.a = ld4g(a + k); c.b = ld4g(b + k); c.c = ld4g(cc + k); }
         return c;
     }
-    __device__ __forceinline__ float4 row(const Coef& c, int p, int P, int k) const {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c.on && p < P) {
-            if (dpool) {
-                const int grp = p / S, s = p - grp * S;
-                const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + (size_t)grp * ldp + k));
-                const float4 d = ld4g(dpool + (size_t)grp * ldp + k);
-                v.x = sl.x == s ? d.x : 0.f; v.y = sl.y == s ? d.y : 0.f; v.z = sl.z == s ? d.z : 0.f; v.w = sl.w == s ? d.w : 0.f;
-            } else {
-                v = ld4g(g + (size_t)p * ldg + k);
-            }
-            if (a) {
-                const float4 yy = ld4g(y + (size_t)p * ldy + k);
-                v.x = fmaf(c.a.x, v.x, fmaf(c.c.x, yy.x, c.b.x)); v.y = fmaf(c.a.y, v.y, fmaf(c.c.y, yy.y, c.b.y));
-                v.z = fmaf(c.a.z, v.z, fmaf(c.c.z, yy.z, c.b.z)); v.w = fmaf(c.a.w, v.w, fmaf(c.c.w, yy.w, c.b.w));
-            }
+    __device__ __forceinline__ Raw fetch(int p, int P, int k, int K) const {
+        Raw r;
+        const int pp = p < P ? p : P - 1, kk = k < K ? k : 0;
+        if (dpool) {   // pooled gradient: [G, ldp] tables, re-used by the S rows of a group (L1 / L2 hits)
+            const int grp = pp / S, s = pp - grp * S;
+            const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + (size_t)grp * ldp + kk));
+            const float4 d = ld4g(dpool + (size_t)grp * ldp + kk);
+            r.g = make_float4(sl.x == s ? d.x : 0.f, sl.y == s ? d.y : 0.f, sl.z == s ? d.z : 0.f, sl.w == s ? d.w : 0.f);
+        } else {
+            r.g = ld4g(g + (size_t)pp * ldg + kk);
+        }
+        r.y = a ? ld4g(y + (size_t)pp * ldy + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return r;
+    }
+    __device__ __forceinline__ float4 finish(const Raw& r, const Coef& c, int p, int P) const {
+        if (!(c.on && p < P)) return make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = r.g;
+        if (a) {
+            v.x = fmaf(c.a.x, v.x, fmaf(c.c.x, r.y.x, c.b.x)); v.y = fmaf(c.a.y, v.y, fmaf(c.c.y, r.y.y, c.b.y));
+            v.z = fmaf(c.a.z, v.z, fmaf(c.c.z, r.y.z, c.b.z)); v.w = fmaf(c.a.w, v.w, fmaf(c.c.w, r.y.w, c.b.w));
         }
         return v;
     }
-    __device__ __forceinline__ float4 load(int p, int P, int k, int K) const { return row(prep(k, K), p, P, k); }
+    __device__ __forceinline__ void prefetch_rows(int p0, int rows, int P) const {
+        if (p0 >= P) return;
+        const size_t n = (size_t)min(rows, P - p0);
+        if (!dpool) o3d_prefetch_l2(g + (size_t)p0 * ldg, n * ldg * sizeof(float));
+        if (a) o3d_prefetch_l2(y + (size_t)p0 * ldy, n * ldy * sizeof(float));
+    }
 };
 
 // ---- epilogues: thread = one output channel `ch`, called once per 32-position column group ------------------
@@ -175,13 +204,13 @@ struct TcFwdEpi {
         mx = -INFINITY; mn = INFINITY; ax = an = 0;
     }
     __device__ __forceinline__ void prefetch(int, int, int, int) {}
-    __device__ __forceinline__ void group(const uint32_t (&r)[32], int ch, int Nw, int pbase, int P) {
+    __device__ __forceinline__ void group(const uint32_t (&r)[16], int ch, int Nw, int pbase, int P) {
         if (ch >= Nw) return;
         float s1 = 0.f, s2 = 0.f;
         const int smask = S - 1;
         float* yp = y ? y + (size_t)pbase * ldy + ch : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
             if (pbase + j >= P) break;
             const float v = __uint_as_float(r[j]) + bv;
             if (yp) yp[(size_t)j * ldy] = v;
@@ -213,7 +242,7 @@ struct TcDgradEpi {
     float* out; int ldo; const float* yprev; int ldyp; const float* scale; const float* shift; int relu;
     double* s1g; double* s2y;
     float sc, sh; double d1, d2;
-    float yv[32];
+    float yv[16];
     __device__ __forceinline__ void begin(int ch, int Nw) {
         d1 = d2 = 0.0;
         sc = (scale && ch < Nw) ? scale[ch] : 1.f;
@@ -223,14 +252,14 @@ struct TcDgradEpi {
     __device__ __forceinline__ void prefetch(int ch, int Nw, int pbase, int P) {
         if (!yprev || ch >= Nw) return;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) yv[j] = (pbase + j < P) ? __ldg(yprev + (size_t)(pbase + j) * ldyp + ch) : 0.f;
+        for (int j = 0; j < 16; ++j) yv[j] = (pbase + j < P) ? __ldg(yprev + (size_t)(pbase + j) * ldyp + ch) : 0.f;
     }
-    __device__ __forceinline__ void group(const uint32_t (&r)[32], int ch, int Nw, int pbase, int P) {
+    __device__ __forceinline__ void group(const uint32_t (&r)[16], int ch, int Nw, int pbase, int P) {
         if (ch >= Nw) return;
         float s1 = 0.f, s2 = 0.f;
         float* op = out + (size_t)pbase * ldo + ch;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
             if (pbase + j >= P) break;
             float v = __uint_as_float(r[j]);
             if (yprev) {
@@ -254,7 +283,7 @@ struct TcDgradEpi {
 // ------------------------------------------------------------------------------------------------------------
 // MT = number of 128-channel tiles one CTA accumulates for the same 128 positions (1 or 2).  With MT = 2 the
 // activation tile is produced once for 256 output channels: producer and epilogue work per MMA halve.
-//   warps: 0 MMA issuer (+TMEM alloc) | 1 weight streamer | 4-7, 8-11 epilogue | 12-15 producers        (512 threads)
+//   warps: 0 MMA issuer (+TMEM alloc) | 1 weight streamer | 4-7, 8-11 epilogue | 2,3,12-17 producers   (576 threads)
 //   MT=2: epilogue warps 4-7 own channel tile 0, warps 8-11 tile 1 (all 128 columns each)
 //   MT=1: warps 4-7 take columns 0-63, warps 8-11 columns 64-127 of the single tile
 template <int MT> struct TcCfg {
@@ -263,11 +292,13 @@ template <int MT> struct TcCfg {
     static constexpr int SMEM = STAGES * STAGE_BYTES_ + 1024 + 256;
     static constexpr uint32_t TMEM = MT == 2 ? 512 : 256;
 };
-constexpr int TC2_THREADS = 512;
+constexpr int TC2_THREADS = 576;   // 18 warps: 0 MMA | 1 weights | 2,3,12-17 producers | 4-11 epilogue
 
+// dbg (profiling experiments only; results are wrong when set): 1 = stream weights for the first tile only,
+// 2 = producers skip the global loads, 4 = epilogue skips its global stores / loads
 template <int MT, class BLoad, class Epi>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
-    pw_tc_kernel(BLoad bl, const uint8_t* __restrict__ wtiles, int P, int K, int Nw, int nkb, Epi epi) {
+    pw_tc_kernel(BLoad bl, const uint8_t* __restrict__ wtiles, int P, int K, int Nw, int nkb, Epi epi, int dbg) {
     using C = TcCfg<MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -284,7 +315,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            o3d_mbar_init(full + s, 128 + 1);
+            o3d_mbar_init(full + s, 256 + 1);
             o3d_mbar_init(empty + s, 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -336,14 +367,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         // ===================================================== weight-tile streamer (bulk copy engine)
         if (lane == 0) {
             int stage = 0, phase = 0;
+            if (!(dbg & 8)) bl.prefetch_rows(blockIdx.x * TC_N, TC_N, P);
             for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
+                if (!(dbg & 8)) bl.prefetch_rows((t + (int)gridDim.x) * TC_N, TC_N, P);   // next tile of this CTA -> L2
                 for (int kb = 0; kb < nkb; ++kb) {
                     o3d_mbar_wait(empty + stage, phase ^ 1);
-                    o3d_mbar_expect_tx(full + stage, MT * 2 * TILE_BYTES);
+                    if ((dbg & 1) && t != (int)blockIdx.x) {
+                        o3d_mbar_arrive(full + stage);
+                    } else {
+                        o3d_mbar_expect_tx(full + stage, MT * 2 * TILE_BYTES);
 #pragma unroll
-                    for (int m = 0; m < MT; ++m)
-                        o3d_bulk_g2s(smem + stage * C::STAGE_BYTES_ + 2 * m * TILE_BYTES,
-                                     wtiles + ((size_t)(mt0 + m) * nkb + kb) * (2 * TILE_BYTES), 2 * TILE_BYTES, full + stage);
+                        for (int m = 0; m < MT; ++m)
+                            o3d_bulk_g2s(smem + stage * C::STAGE_BYTES_ + 2 * m * TILE_BYTES,
+                                         wtiles + ((size_t)(mt0 + m) * nkb + kb) * (2 * TILE_BYTES), 2 * TILE_BYTES, full + stage);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -353,64 +390,67 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int grp = (warp - 4) >> 2;              // 0: warps 4-7, 1: warps 8-11
         const int m = MT == 2 ? grp : 0;              // channel tile inside the CTA
-        const int cg0 = MT == 2 ? 0 : grp * 2, cg1 = MT == 2 ? 4 : grp * 2 + 2;   // 32-column groups to handle
+        const int cg0 = MT == 2 ? 0 : grp * 4, cg1 = MT == 2 ? 8 : grp * 4 + 4;   // 16-column groups to handle
         const int ch = (mt0 + m) * TC_M + q * 32 + lane;
         epi.begin(ch, Nw);
+        const int Nw_e = (dbg & 4) ? 0 : Nw;          // dbg: ch >= Nw_e -> the epilogue body is skipped
         int acc = 0, aphase = 0;
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
-            epi.prefetch(ch, Nw, t * TC_N + cg0 * 32, P);
+            epi.prefetch(ch, Nw_e, t * TC_N + cg0 * 16, P);
             o3d_mbar_wait(tfull + acc, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + m) * TC_N);
 #pragma unroll 1
             for (int cg = cg0; cg < cg1; ++cg) {
-                uint32_t r[32];
-                tmem_ld32(taddr + cg * 32, r);
-                epi.group(r, ch, Nw, t * TC_N + cg * 32, P);
-                if (cg + 1 < cg1) epi.prefetch(ch, Nw, t * TC_N + (cg + 1) * 32, P);
+                uint32_t r[16];
+                tmem_ld16(taddr + cg * 16, r);
+                epi.group(r, ch, Nw_e, t * TC_N + cg * 16, P);
+                if (cg + 1 < cg1) epi.prefetch(ch, Nw_e, t * TC_N + (cg + 1) * 16, P);
             }
             tc_fence_before();
             o3d_mbar_arrive(tempty + acc);
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         epi.end(ch, Nw);
-    } else if (warp >= 12) {
-        // ===================================================== activation-operand producers (128 threads)
-        const int pt = threadIdx.x - 384;             // 0..127
-        const int chunk = pt & 7;                     // 16-byte chunk (4 channels) inside the 128-byte row
-        const int row0 = pt >> 3;                     // rows row0 + 16*i
+    } else {
+        // ===================================================== activation-operand producers (8 warps, 256 threads)
+        // Per k-block: [raw rows of kb already in registers] -> wait for the stage -> transform, hi/lo split, swizzled
+        // st.shared -> fence + arrive -> issue the raw loads of kb+1 (all back to back, nothing depends on them until
+        // the next iteration, so they fly while the MMA warp works through the stages ahead).
+        const int pw = warp < 4 ? warp - 2 : warp - 10;   // producer warp 0..7
+        const int pt = pw * 32 + lane;                    // 0..255
+        const int chunk = pt & 7;                         // 16-byte chunk (4 channels) inside the 128-byte row
+        const int row0 = pt >> 3;                         // rows row0 + 32*i, i < 4
         int stage = 0, phase = 0;
+        if (dbg & 2) P = 0;                               // dbg: nothing is loaded
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
             const int p0 = t * TC_N;
-            float4 v[8];
-            {
-                const auto c = bl.prep(chunk * 4, K);
+            typename BLoad::Raw raw[4];
+            typename BLoad::Coef cf = bl.prep(chunk * 4, K);
+            if (P > 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = bl.row(c, p0 + row0 + 16 * i, P, chunk * 4);
+                for (int i = 0; i < 4; ++i) raw[i] = bl.fetch(p0 + row0 + 32 * i, P, chunk * 4, K);
             }
             for (int kb = 0; kb < nkb; ++kb) {
-                float4 nx[8];
-                const bool more = kb + 1 < nkb;
-                if (more) {
-                    const int k = (kb + 1) * TC_K + chunk * 4;
-                    const auto c = bl.prep(k, K);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) nx[i] = bl.row(c, p0 + row0 + 16 * i, P, k);
-                }
                 o3d_mbar_wait(empty + stage, phase ^ 1);
                 uint8_t* xhi = smem + stage * C::STAGE_BYTES_ + 2 * MT * TILE_BYTES;
                 uint8_t* xlo = xhi + TILE_BYTES;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t off = sw128(row0 + 16 * i, chunk);
-                    *reinterpret_cast<float4*>(xhi + off) = hi_part(v[i]);
-                    *reinterpret_cast<float4*>(xlo + off) = lo_part(v[i]);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = P > 0 ? bl.finish(raw[i], cf, p0 + row0 + 32 * i, P) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const uint32_t off = sw128(row0 + 32 * i, chunk);
+                    *reinterpret_cast<float4*>(xhi + off) = hi_part(v);
+                    *reinterpret_cast<float4*>(xlo + off) = lo_part(v);
                 }
                 o3d_fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
                 o3d_mbar_arrive(full + stage);
-                if (more) {
+                if (kb + 1 < nkb) {
+                    const int k = (kb + 1) * TC_K + chunk * 4;
+                    cf = bl.prep(k, K);
+                    if (P > 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = nx[i];
+                        for (int i = 0; i < 4; ++i) raw[i] = bl.fetch(p0 + row0 + 32 * i, P, k, K);
+                    }
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -427,32 +467,70 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
 // ------------------------------------------------------------------------------------------------------------
 // wgrad on the tensor core:  dW[m, n] += sum_p dY[p, m] * X[p, n]  over this CTA's slice of positions.
 // Both operands are position-major in global memory (channels contiguous), i.e. "MN-major" for a GEMM whose K is the
-// position index.  They are written to shared memory in the MN-major SWIZZLE_128B canonical layout — atoms of
-// 8 positions x 32 channels (1 KB), 16-byte chunk index XOR (position % 8) — so the producers copy coalesced float4
-// rows without any transposition; the instruction descriptor marks A and B as MN-major.
-//   tile [32 positions x 128 channels]:  atom(cb, pb) at (cb + 4*pb) * 1024,  cb = channel/32, pb = position/8
-//   descriptor for k-step pb: start = tile + pb*4096, LBO = 1024 (next 32-channel block), SBO = 4096 (next 8 positions)
+// position index.  For 32-bit (tf32) MN-major operands the tensor core accepts exactly one shared-memory layout,
+// SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom): atoms of 4 positions x 32 channels (512 B; one
+// position = one 128-byte row), the 32-byte chunk index XOR-ed with (position % 4).  The producers copy coalesced
+// float4 rows straight into it — no transposition — and the instruction descriptor marks A and B as MN-major.
+//   tile [32 positions x 128 channels]:  atom(cb, pq) at (cb + 4*pq) * 512,  cb = channel/32, pq = position/4
+//   descriptor for k-step ks (8 positions = 2 atoms along K): start = tile + ks*4096,
+//   LBO = 512 (next 32-channel block), SBO = 2048 (next 4 positions)
 constexpr int WG_THREADS = 512;
 constexpr int WG_SMEM = TC_STAGES * STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)(1024 >> 4) << 16;   // leading byte offset: between 32-channel blocks
-    d |= (uint64_t)(4096 >> 4) << 32;   // stride byte offset : between 8-position blocks
+    d |= (uint64_t)(512 >> 4) << 16;    // leading byte offset: between 32-channel blocks
+    d |= (uint64_t)(2048 >> 4) << 32;   // stride byte offset : between 4-position blocks
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;             // SWIZZLE_128B_BASE32B
     return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
     return make_idesc(M, N) | (1u << 15) | (1u << 16);
 }
 __device__ __forceinline__ uint32_t sw128_mn(int p_local, int c4) {   // c4 = float4 index along the 128 channels
-    return (uint32_t)(((c4 >> 3) + 4 * (p_local >> 3)) * 1024 + (p_local & 7) * 128 + (((c4 & 7) ^ (p_local & 7)) << 4));
+    const int cb = c4 >> 3, c32 = (c4 & 7) >> 1, half = c4 & 1, j0 = p_local & 3;
+    return (uint32_t)((cb + 4 * (p_local >> 2)) * 512 + j0 * 128 + ((c32 ^ j0) << 5) + (half << 4));
+}
+
+// One operand's producer loop of the wgrad kernel: raw loads of k-block kb+1 are issued right after k-block kb has been
+// handed to the tensor core; transform + hi/lo split happen at store time.
+template <class L>
+__device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int tile_off, uint64_t* full, uint64_t* empty,
+                                              int pt, int c_base, int CH, int pbeg, int pend, int nkb) {
+    const int c4 = pt & 31, prow0 = pt >> 5;      // rows prow0 + 4*i
+    const int ch0 = c_base + c4 * 4;
+    const typename L::Coef cf = ld.prep(ch0, CH);
+    typename L::Raw raw[8];
+    int stage = 0, phase = 0;
+    if (nkb > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) raw[i] = ld.fetch(pbeg + prow0 + 4 * i, pend, ch0, CH);
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+        o3d_mbar_wait(empty + stage, phase ^ 1);
+        uint8_t* hi = smem + stage * STAGE_BYTES + tile_off;
+        uint8_t* lo = hi + TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = ld.finish(raw[i], cf, pbeg + kb * TC_K + prow0 + 4 * i, pend);
+            const uint32_t off = sw128_mn(prow0 + 4 * i, c4);
+            *reinterpret_cast<float4*>(hi + off) = hi_part(v);
+            *reinterpret_cast<float4*>(lo + off) = lo_part(v);
+        }
+        o3d_fence_proxy_async();
+        o3d_mbar_arrive(full + stage);
+        if (kb + 1 < nkb) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) raw[i] = ld.fetch(pbeg + (kb + 1) * TC_K + prow0 + 4 * i, pend, ch0, CH);
+        }
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+    }
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-    pw_wgrad_tc_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ dW, int lddw) {
+    pw_wgrad_tc_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ dW, int lddw, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
@@ -481,7 +559,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        const uint32_t idesc = make_idesc_mn(TC_M, TC_N);
+        const uint32_t idesc = (dbg & 16) ? make_idesc(TC_M, TC_N) : make_idesc_mn(TC_M, TC_N);
         int stage = 0, phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             o3d_mbar_wait(full + stage, phase);
@@ -493,6 +571,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
                     const uint32_t o = pb * 4096;
                     const uint64_t ahi = make_desc_mn(sb + o), alo = make_desc_mn(sb + TILE_BYTES + o);
                     const uint64_t bhi = make_desc_mn(sb + 2 * TILE_BYTES + o), blo = make_desc_mn(sb + 3 * TILE_BYTES + o);
+                    if (dbg & 32) continue;
                     umma_tf32(tmem_base, alo, bhi, idesc, (kb | pb) != 0);
                     umma_tf32(tmem_base, ahi, blo, idesc, 1u);
                     umma_tf32(tmem_base, ahi, bhi, idesc, 1u);
@@ -502,6 +581,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
             }
             __syncwarp();
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // stream the position rows of this slice into L2, 16 k-blocks (512 rows) at a time
+            for (int p = pbeg; p < pend; p += 512) {
+                da.prefetch_rows(p, 512, pend);
+                xb.prefetch_rows(p, 512, pend);
+            }
         }
     } else if (warp >= 4 && warp < 8) {
         if (nkb > 0) {
@@ -525,43 +611,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         }
     } else if (warp >= 8) {
         // producers: warps 8-11 -> A (dY, channels m0..), warps 12-15 -> B (X, channels n0..)
-        const bool isA = warp < 12;
         const int pt = (threadIdx.x - 256) & 127;
-        const int c4 = pt & 31, prow0 = pt >> 5;      // rows prow0 + 4*i
-        int stage = 0, phase = 0;
-        float4 v[8];
-        auto ldrow = [&](int kb, int i) {
-            const int p = pbeg + kb * TC_K + prow0 + 4 * i;
-            return isA ? da.load(p, pend, m0 + c4 * 4, M) : xb.load(p, pend, n0 + c4 * 4, N);
-        };
-        if (nkb > 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = ldrow(0, i);
-        }
-        for (int kb = 0; kb < nkb; ++kb) {
-            float4 nx[8];
-            const bool more = kb + 1 < nkb;
-            if (more) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) nx[i] = ldrow(kb + 1, i);
-            }
-            o3d_mbar_wait(empty + stage, phase ^ 1);
-            uint8_t* hi = smem + stage * STAGE_BYTES + (isA ? 0 : 2 * TILE_BYTES);
-            uint8_t* lo = hi + TILE_BYTES;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t off = sw128_mn(prow0 + 4 * i, c4);
-                *reinterpret_cast<float4*>(hi + off) = hi_part(v[i]);
-                *reinterpret_cast<float4*>(lo + off) = lo_part(v[i]);
-            }
-            o3d_fence_proxy_async();
-            o3d_mbar_arrive(full + stage);
-            if (more) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = nx[i];
-            }
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-        }
+        if (warp < 12) wgrad_produce(da, smem, 0, full, empty, pt, m0, M, pbeg, pend, nkb);
+        else wgrad_produce(xb, smem, 2 * TILE_BYTES, full, empty, pt, n0, N, pbeg, pend, nkb);
     }
     tc_fence_before();
     __syncthreads();
@@ -587,6 +639,8 @@ __global__ void w_pretile_kernel(const float* __restrict__ W, int ld, int rows, 
     }
 }
 
+int g_tc_debug = 0, g_tc_force_mt = 0;
+
 template <int MT, class BLoad, class Epi>
 int launch_tc_mt(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cudaStream_t st, const char* name) {
     auto kern = pw_tc_kernel<MT, BLoad, Epi>;
@@ -598,7 +652,7 @@ int launch_tc_mt(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi,
     int gx = o3d_num_sms() / gy;
     if (gx < 1) gx = 1;
     if (gx > n_ptiles) gx = n_ptiles;
-    kern<<<dim3(gx, gy), TC2_THREADS, TcCfg<MT>::SMEM, st>>>(bl, wtiles, P, K, Nw, nkb, epi);
+    kern<<<dim3(gx, gy), TC2_THREADS, TcCfg<MT>::SMEM, st>>>(bl, wtiles, P, K, Nw, nkb, epi, g_tc_debug);
     O3D_CHECK_LAUNCH(name);
     return O3D_OK;
 }
@@ -607,11 +661,13 @@ int launch_tc_mt(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi,
 template <class BLoad, class Epi>
 int launch_tc(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cudaStream_t st, const char* name) {
     const int mt = (Nw + TC_M - 1) / TC_M;
-    if (mt % 2 == 0) return launch_tc_mt<2>(bl, wtiles, P, K, Nw, epi, st, name);
+    if (mt % 2 == 0 && g_tc_force_mt != 1) return launch_tc_mt<2>(bl, wtiles, P, K, Nw, epi, st, name);
     return launch_tc_mt<1>(bl, wtiles, P, K, Nw, epi, st, name);
 }
 
 }  // namespace
+
+extern "C" void o3d_debug_set(int tc_debug, int force_mt) { g_tc_debug = tc_debug; g_tc_force_mt = force_mt; }
 
 extern "C" long long o3d_pw_tc_wtile_bytes(int rows, int K) {
     const long long mt = (rows + TC_M - 1) / TC_M, nkb = (K + TC_K - 1) / TC_K;
@@ -679,7 +735,7 @@ extern "C" int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy,
     int chunk = (P + splits - 1) / splits;
     chunk = ((chunk + TC_K - 1) / TC_K) * TC_K;
     splits = (P + chunk - 1) / chunk;
-    pw_wgrad_tc_kernel<<<dim3(splits, nt, mt), WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(da, xb, P, Cout, Cin, chunk, dw, lddw);
+    pw_wgrad_tc_kernel<<<dim3(splits, nt, mt), WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(da, xb, P, Cout, Cin, chunk, dw, lddw, g_tc_debug);
     O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc");
     return O3D_OK;
 }

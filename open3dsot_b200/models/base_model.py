@@ -59,3 +59,12 @@ class MatchingBaseModel(BaseModel):
                                     box_label[:, None, :4].expand_as(estimation_boxes[:, :, :4]), reduction='none')
         loss_box = torch.sum(loss_box.mean(2) * objectness_label) / (objectness_label.sum() + 1e-6)
         return {"loss_objective": loss_objective, "loss_box": loss_box, "loss_seg": loss_seg, "loss_vote": loss_vote}
+
+
+class MotionBaseModel(BaseModel):
+    """Base of the motion-centric models (models/base_model.py:250-303); the input-dict construction for tracking
+    evaluation (:255-303) needs the dataset stack and is out of scope."""
+
+    def __init__(self, config, **kwargs):
+        super().__init__(config, **kwargs)
+        self.save_hyperparameters()

@@ -55,10 +55,24 @@ def install_stubs():
         def __init__(self, *a, **k):
             super().__init__()
 
+        def forward(self, *a, **k):          # logging-only metric objects of the reference
+            return torch.zeros(2)
+
     mod("torchmetrics", Metric=_Metric, Accuracy=_Metric)
     nus = mod("nuscenes"); nus.utils = mod("nuscenes.utils")
     nus.utils.geometry_utils = mod("nuscenes.utils.geometry_utils")
-    ds = mod("datasets"); ds.points_utils = mod("datasets.points_utils")
+    sys.modules["nuscenes.utils"] = nus.utils
+    # datasets.points_utils: load the reference's own file (its torch box transforms are used by M2TRACK.forward);
+    # its numpy-side imports (pyquaternion, nuscenes, datasets.data_classes) are inert stand-ins
+    mod("pyquaternion", Quaternion=object)
+    ds = mod("datasets"); ds.__path__ = []
+    mod("datasets.data_classes", PointCloud=object, Box=object)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("datasets.points_utils", os.path.join(REF, "datasets", "points_utils.py"))
+    pu = importlib.util.module_from_spec(spec)
+    sys.modules["datasets.points_utils"] = pu
+    spec.loader.exec_module(pu)
+    ds.points_utils = pu
     ut = mod("utils")
     ut.metrics = mod("utils.metrics", TorchSuccess=_Metric, TorchPrecision=_Metric,
                      estimateOverlap=None, estimateAccuracy=None)
@@ -170,6 +184,35 @@ def gen_model(name, cfg_file, B, M, N, out, seed):
     out[f"{name}_eval_cla"] = np_(ep["estimation_cla"])
 
 
+def gen_m2track(out):
+    """M2_track_kitti.yaml (BASELINE.json configs[2]) at B=4, point_sample_size 256: forward, loss, gradient norms."""
+    from models import get_model
+    from open3dsot_b200.datasets.synthetic import synthetic_motion_batch
+    cfg = EasyDict(load_yaml(os.path.join(ROOT, "cfgs", "M2_track_kitti.yaml")))
+    net = get_model(cfg.net_model)(cfg)
+    net.load_state_dict(det_state_dict(net.state_dict(), seed=31), strict=False)
+    net.train()
+    net.log = lambda *a, **k: None
+    net.logger.experiment.add_scalars = lambda *a, **k: None
+    batch = synthetic_motion_batch(4, 256, seed=77)
+    loss = net.training_step({k: v.clone() for k, v in batch.items()}, 0)
+    loss.backward()
+    out["m2_loss"] = np_(loss)
+    sd = dict(net.named_parameters())
+    out["m2_gradnorms"] = np.array([float(p.grad.norm()) if p.grad is not None else 0.0 for _, p in sorted(sd.items())],
+                                   dtype=np.float64)
+    net.load_state_dict(det_state_dict(net.state_dict(), seed=31), strict=False)
+    with torch.no_grad():
+        ep = net({k: v.clone() for k, v in batch.items()})
+    for k in ("estimation_boxes", "seg_logits", "motion_pred", "aux_estimation_boxes", "pred_bc", "motion_cls"):
+        out[f"m2_{k}"] = np_(ep[k])
+    net.eval()
+    net.load_state_dict(det_state_dict(net.state_dict(), seed=31), strict=False)
+    with torch.no_grad():
+        ep = net({k: v.clone() for k, v in batch.items()})
+    out["m2_eval_boxes"] = np_(ep["estimation_boxes"])
+
+
 def main():
     assert os.path.isdir(REF), "golden vectors can only be generated where /root/reference exists"
     install_stubs()
@@ -180,6 +223,7 @@ def main():
     models = {}
     gen_model("bat", "BAT_Car.yaml", 2, 256, 512, models, seed=21)
     gen_model("p2b", "P2B_Car.yaml", 1, 256, 512, models, seed=22)   # BASELINE.json configs[0]
+    gen_m2track(models)
     np.savez_compressed(os.path.join(HERE, "ref_models.npz"), **models)
     for f in ("ref_modules.npz", "ref_models.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

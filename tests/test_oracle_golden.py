@@ -136,3 +136,34 @@ def test_whole_model_forward_loss_grads(gmod, name, cfg_file, B, seed):
             assert rel(sd[p].grad[:16], gmod[key]) < 5e-4, p
     norms = np.array([float(sd[k].grad.norm()) for k in sorted(pnames)])
     assert np.allclose(norms, gmod[f"{name}_gradnorms"], rtol=2e-3, atol=1e-7)
+
+
+def test_m2track_mirror_matches_reference_on_cpu(gmod):
+    """M2-Track has no pointnet2 ops, so the host mirror (composed mode = plain torch) can be held against the
+    reference's own run on CPU: forward, loss and gradient norms (BASELINE.json configs[2], reduced to B=4 / 256 pts)."""
+    from open3dsot_b200 import runtime
+    from open3dsot_b200.datasets.synthetic import synthetic_motion_batch
+    cfg = load_config(os.path.join(ROOT, "cfgs", "M2_track_kitti.yaml"))
+    net = get_model(cfg.net_model)(cfg)
+    base = det_state_dict(net.state_dict(), seed=31)
+    batch = synthetic_motion_batch(4, 256, seed=77)
+    with runtime.composed_mode():
+        net.load_state_dict(base)
+        net.train()
+        with torch.no_grad():
+            ep = net({k: v.clone() for k, v in batch.items()})
+        for k in ("estimation_boxes", "seg_logits", "motion_pred", "aux_estimation_boxes", "pred_bc", "motion_cls"):
+            assert rel(ep[k], gmod[f"m2_{k}"]) < RTOL, k
+        net.load_state_dict(base)
+        net.eval()
+        with torch.no_grad():
+            ep = net({k: v.clone() for k, v in batch.items()})
+        assert rel(ep["estimation_boxes"], gmod["m2_eval_boxes"]) < RTOL
+        net.load_state_dict(base)
+        net.train()
+        loss = net.training_step({k: v.clone() for k, v in batch.items()}, 0)
+        assert rel(loss, gmod["m2_loss"]) < RTOL
+        loss.backward()
+    sd = dict(net.named_parameters())
+    norms = np.array([float(p.grad.norm()) if p.grad is not None else 0.0 for _, p in sorted(sd.items())])
+    assert np.allclose(norms, gmod["m2_gradnorms"], rtol=2e-3, atol=1e-6 * float(gmod["m2_gradnorms"].max()))
