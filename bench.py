@@ -144,10 +144,8 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def roofline_probe(dev, batch_pairs):
-    """Time the dominant bandwidth-bound kernel alone (CUDA events on the launch stream, L2 flushed by size:
-    output >> 126 MB).  Kernel: fused ball query + grouping of the SA3 search layer shape (the largest grouped
-    tensor of the model): xyz (B,256,3), features (B,256,256) -> grouped (B,128,32,260)."""
+def gather_roofline(dev, batch_pairs):
+    """The fused ball-query + grouping kernel (HBM write-bound) alone, SA3-search shape, output >> L2."""
     from open3dsot_b200 import ops
     from open3dsot_b200.datasets.synthetic import synthetic_siamese_batch
     B = max(batch_pairs, 48) * 4           # 192 clouds -> 816 MB written per launch (> L2)
@@ -175,6 +173,58 @@ def roofline_probe(dev, batch_pairs):
             "peak": peaks["hbm_gbs"], "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
             "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
             "algorithmic_bytes_per_launch": alg_bytes}
+
+
+def roofline_probe(dev, batch_pairs):
+    """The dominant kernel family of the step — the point-wise MLP GEMM (pw_tc_kernel, forward, SA3-search layer:
+    196608 positions x 256 -> 256 channels) — timed alone with CUDA events on its stream through the C ABI.
+    It is bounded by BOTH roofs at this shape (arithmetic intensity 64 FLOP/B of fp32 activations, 3 tensor passes):
+      tensor : algorithmic 2*P*K*N FLOP vs measured bf16 peak / 2 (TF32 rate) / 3 (3xTF32 passes)
+      hbm    : algorithmic bytes (X read + Y written once, fp32) vs the measured copy bandwidth
+    `frac` is reported against the TIGHTER of the two (the larger time bound)."""
+    import ctypes
+    from open3dsot_b200 import _lib
+    L = _lib.lib()
+    P, K, N = max(batch_pairs, 48) * 128 * 32, 256, 256
+    x = torch.randn(P, K, device=dev)
+    w = torch.randn(N, K, device=dev) * 0.05
+    y = torch.empty(P, N, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    tiles = torch.empty(int(L.o3d_pw_tc_wtile_bytes(N, K)), dtype=torch.uint8, device=dev)
+    _lib.check(L.o3d_pw_tc_pretile(w.data_ptr(), K, N, K, tiles.data_ptr(), st), "pretile")
+    stat = torch.zeros(2 * N, dtype=torch.float64, device=dev)
+
+    def launch():
+        _lib.check(L.o3d_pw_fwd_tc(x.data_ptr(), K, None, None, 0, tiles.data_ptr(), None, P, K, N, y.data_ptr(), N,
+                                   stat.data_ptr(), stat.data_ptr() + 8 * N, 0, None, None, None, N, st), "o3d_pw_fwd_tc")
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    peaks, how = measured_peaks()
+    flops = 2.0 * P * K * N
+    alg_bytes = 4.0 * P * (K + N)                      # 403 MB per launch: larger than the 126 MB L2
+    tf = flops / (ms * 1e-3) / 1e12
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    tensor_peak = peaks["bf16_tflops"] / 2.0 / 3.0      # TF32 runs at half the bf16 rate; 3 passes per product
+    t_tensor, t_hbm = flops / (tensor_peak * 1e12), alg_bytes / (peaks["hbm_gbs"] * 1e9)
+    bound = "tensor" if t_tensor >= t_hbm else "hbm"
+    return {"kernel": "pw_tc_kernel<2,TcAct,TcFwdEpi> (SA3-search layer: P=%d, K=256, N=256, 3xTF32)" % P,
+            "bound": bound, "achieved": tf if bound == "tensor" else gbs,
+            "peak": tensor_peak if bound == "tensor" else peaks["hbm_gbs"],
+            "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+            "frac": (tf / tensor_peak) if bound == "tensor" else (gbs / peaks["hbm_gbs"]),
+            "peak_source": how + " MEASURED_PEAKS.json: bf16_tflops/2/3 (TF32 rate, three passes) and hbm_gbs (burst)",
+            "traffic": None, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
+            "algorithmic_bytes_per_launch": alg_bytes, "achieved_tflops_fp32_equiv": tf, "achieved_gbs": gbs,
+            "frac_of_tensor_roof": tf / tensor_peak, "frac_of_hbm_roof": gbs / peaks["hbm_gbs"]}
 
 
 def run_ours(args):
@@ -265,6 +315,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     roof = roofline_probe(dev, args.batch)
+    roof_gather = gather_roofline(dev, args.batch)
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(args.cpu_batch, args.cpu_steps)
@@ -282,7 +333,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": launches, "wall_s_timed_region": wall,
             "e2e": {"value": pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / args.steps * 1e3},
-            "roofline": roof, "cpu_baseline": cb}
+            "roofline": roof, "roofline_gather": roof_gather, "cpu_baseline": cb}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

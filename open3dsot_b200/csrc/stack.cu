@@ -14,6 +14,9 @@
 namespace {
 
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+// channels handled by the tensor-core kernels: whole 128-tiles, or one partial tile for 64 <= c < 128; the rest
+// (xyz / box-cloud extras of a first layer) goes through the exact CUDA-core kernel
+inline int tc_main(int c) { return c >= 128 ? (c / 128) * 128 : (c >= 64 ? c : 0); }
 inline int r4(int x) { return (x + 3) & ~3; }
 
 // ---- weight packing -----------------------------------------------------------------------------------------
@@ -85,9 +88,9 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     for (int l = 0; l < p.n; ++l) {
         p.Nw[l] = r4(d->cout[l]);
         p.K[l] = l == 0 ? d->K0 : p.Nw[l - 1];
-        p.tc_f[l] = (d->use_tc & 1) && p.Nw[l] >= 128 && p.Nw[l] % 128 == 0 && p.K[l] >= 32 && d->P >= 128 &&
+        p.tc_f[l] = (d->use_tc & 1) && (p.Nw[l] % 128 == 0 || p.Nw[l] == 64) && p.K[l] >= 32 && d->P >= 128 &&
                     !(l == d->n_layers - 1 && d->S > 0 && 64 % d->S != 0);
-        p.tc_b[l] = (d->use_tc & 1) && p.K[l] >= 128 && p.Nw[l] >= 32 && d->P >= 128;
+        p.tc_b[l] = (d->use_tc & 1) && p.K[l] >= 64 && p.Nw[l] >= 32 && d->P >= 128;
     }
     // statistics block first (one memset)
     p.stat_all = o;
@@ -117,7 +120,7 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     for (int l = 0; l < p.n; ++l) {
         p.coef[l] = o; o += al(sizeof(float) * 5 * p.Nw[l]);
         p.dwp[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]);
-        p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes((p.K[l] / 128) * 128, p.Nw[l]));
+        p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(tc_main(p.K[l]), p.Nw[l]));
         if ((size_t)p.K[l] > maxk) maxk = p.K[l];
     }
     size_t maxn = 0;
@@ -286,11 +289,11 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         if (d->d_weight[l]) {
             float* dwp = at<float>(wb, p.dwp[l]);
             O3D_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)Nl * K, st), "o3d_stack_backward: memset dW");
-            const bool tcw = (d->use_tc & 2) && Nl >= 128 && K >= 128 && p.P >= 4096;
+            const bool tcw = (d->use_tc & 2) && Nl >= 64 && K >= 64 && p.P >= 4096;
             if (tcw) {
                 // tensor-core part: the first floor(K/128)*128 input channels; ragged tail (xyz / box-cloud extras)
                 // goes through the exact CUDA-core kernel on the remaining columns
-                const int Kmain = (K / 128) * 128;
+                const int Kmain = tc_main(K);
                 rc = o3d_pw_wgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, Kmain, dwp, K,
                                      stream);
                 if (rc) return rc;
@@ -315,7 +318,7 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
             if (p.tc_b[l]) {
                 // tensor cores on the first floor(K/128)*128 input channels, exact CUDA-core kernel on the ragged tail
                 // (the xyz / box-cloud extras of a first layer)
-                const int Km = (K / 128) * 128;
+                const int Km = tc_main(K);
                 void* tiles = wb + p.btiles[l];
                 rc = o3d_pw_tc_pretile(at<float>(wf, p.wt[l]), Nl, Km, Nl, tiles, stream);
                 if (rc) return rc;

@@ -49,6 +49,10 @@ def init_distributed(backend=None):
     return rank, world, local
 
 
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def broadcast_parameters(flat: FlatParams, module: torch.nn.Module):
     """Rank 0's parameters and buffers become everyone's (DDP does the same at construction)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

@@ -46,13 +46,20 @@ class TrainStep:
         self.static_loss = None
         self.calls = 0
 
-    def _eager(self, batch):
+    def _fwd_bwd(self, batch):
         self.flat.zero_grad()
         loss = self.model.training_step(dict(batch), 0)
         loss.backward()
-        ddp.allreduce_gradients(self.flat)
-        self.opt.step()
         return loss.detach()
+
+    def _finish(self):
+        ddp.allreduce_gradients(self.flat)      # one NCCL all-reduce of the flat bucket (no-op on a single rank)
+        self.opt.step()
+
+    def _eager(self, batch):
+        loss = self._fwd_bwd(batch)
+        self._finish()
+        return loss
 
     def _capture(self, batch):
         self.static_batch = {k: v.clone() for k, v in batch.items()}
@@ -62,9 +69,14 @@ class TrainStep:
             for _ in range(2):                       # settle allocator / lazy initialisation on the capture stream
                 self._eager(self.static_batch)
         torch.cuda.current_stream().wait_stream(s)
+        # single rank: the whole step (incl. Adam) is one graph; multi-rank: forward+backward are captured and the
+        # gradient all-reduce + Adam are enqueued right behind the replay (NCCL stays outside the capture)
         self.graph = torch.cuda.CUDAGraph()
+        self.graph_has_update = not ddp.is_distributed()
         with torch.cuda.graph(self.graph):
-            self.static_loss = self._eager(self.static_batch)
+            self.static_loss = self._fwd_bwd(self.static_batch)
+            if self.graph_has_update:
+                self._finish()
 
     def step(self, batch):
         self.calls += 1
@@ -75,4 +87,6 @@ class TrainStep:
         for k, v in batch.items():
             self.static_batch[k].copy_(v, non_blocking=True)
         self.graph.replay()
+        if not self.graph_has_update:
+            self._finish()
         return self.static_loss

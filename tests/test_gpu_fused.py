@@ -144,6 +144,7 @@ TC_CASES = [
     ("tc_sa3", [260, 256, 256, 256], 32 * 37, 32),      # ragged P (1184 = 9.25 tiles), K = 260 (9 k-blocks, tail)
     ("tc_bax", [268, 256, 256, 256], 4 * 160, 4),
     ("tc_dense", [64, 128, 256], 300, 0),
+    ("tc_sa1", [4, 64, 64, 128], 32 * 150, 32),         # 64-channel layers: one partial 128-row tile
 ]
 
 
