@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=48, help="pairs per GPU (BAT_Car.yaml config 2: 48)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=4, help="pairs per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="pairs per CPU-baseline step (bounded sample)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=None, help="override O3D_FUSED (1 = fused kernels, 0 = composed)")
@@ -95,7 +95,8 @@ def cpu_baseline(batch_pairs, steps, seed=20260924):
     from open3dsot_b200.datasets.synthetic import synthetic_siamese_batch
     from open3dsot_b200.models import get_model
     from oracle import modules as om
-    cores = os.cpu_count() or 1
+    # torch's CPU kernels stop scaling (and then slow down) on these small per-pair tensors: cap the thread pool
+    cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     cfg = load_config(CFG_FILE)
     torch.manual_seed(0)
@@ -126,7 +127,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args.cpu_batch, max(1, min(args.steps, 5)))
+    # bounded sample: one "step" = the oracle's BAT forward+backward on `cpu_batch` pairs; at most ~150 s in total
+    t0 = time.perf_counter()
+    probe = cpu_baseline(1, 1)
+    per_pair = probe["ms_per_step"] * 1e-3
+    budget = 150.0 - (time.perf_counter() - t0)
+    steps = max(1, min(args.steps, int(budget / max(per_pair * args.cpu_batch, 1e-3)) - 1))
+    cb = cpu_baseline(args.cpu_batch, steps)
+    cb["sample"] += f" ({steps} of the requested {args.steps} steps fit the time box)"
     line = {"metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",

@@ -335,3 +335,69 @@ def p2b_xcorr_forward(xc, template_feature, search_feature, template_xyz):
     pooled = mlp_stack(fusion.reshape(B * n2 * n1, fusion.shape[3]), parse_stack(xc.mlp), n1, xc.training)
     out = from_channels_last(pooled.reshape(B, n2, pooled.shape[1]))
     return seq_forward(xc.fea_layer, out)
+
+
+# ---------------------------------------------------------------------------------------------- M2-Track dense nets
+def rows_forward(module, x):
+    """Linear/BN/ReLU head (nn.Sequential) applied to x (B, C) -> (B, Cout)."""
+    C = x.shape[1]
+    if C % 4:
+        x = F.pad(x, (0, _r4(C) - C))
+    return mlp_stack(x.contiguous(), parse_stack(module), 0, module.training)
+
+
+def _block_specs(blocks):
+    """nn.Sequential(Conv1d, BatchNorm1d, ReLU) blocks (models/backbone/pointnet.py:160-181) -> layer specs."""
+    return [_LayerSpec(b[0].weight, b[0].bias, b[1], True) for b in blocks]
+
+
+def _pool_groups(P_per_cloud):
+    for s in (64, 32, 16, 8, 4, 2, 1):
+        if P_per_cloud % s == 0:
+            return s
+    return 1
+
+
+def minipointnet_forward(net, x):
+    """Fused MiniPointNet.forward (models/backbone/pointnet.py:91-141): per-point conv/BN/ReLU stack, global max over
+    the N points (max over groups of <= 64 positions in the GEMM epilogue, then over the groups), FC/BN/ReLU head."""
+    B, C, N = x.shape
+    mods = list(net.features)
+    cut = next(i for i, m in enumerate(mods) if isinstance(m, nn.AdaptiveMaxPool1d))
+    per_point = nn.Sequential(*mods[:cut])
+    head = nn.Sequential(*[m for m in mods[cut + 1:] if not isinstance(m, nn.Flatten)])
+    per_point.train(net.training)
+    head.train(net.training)
+    cl = to_channels_last(x)
+    S = _pool_groups(N)
+    pooled = mlp_stack(cl.view(B * N, cl.shape[2]), parse_stack(per_point), S, net.training)       # (B*N/S, C')
+    feat = pooled.view(B, N // S, pooled.shape[1]).max(dim=1)[0]
+    if len(list(head.children())):
+        feat = mlp_stack(feat.contiguous(), parse_stack(head), 0, net.training)
+    if net.output_size > 0:
+        feat = mlp_stack(feat.contiguous(), [_LayerSpec(net.fc.weight, net.fc.bias, None, False)], 0, net.training)
+    return feat
+
+
+def segpointnet_forward(net, x):
+    """Fused SegPointNet.forward (models/backbone/pointnet.py:183-204)."""
+    B, C, N = x.shape
+    cl = to_channels_last(x)
+    P = B * N
+    blocks = list(net.seq_per_point)
+    second = mlp_stack(cl.view(P, cl.shape[2]), _block_specs(blocks[:2]), 0, net.training)           # (P, 64)
+    S = _pool_groups(N)
+    pooled = mlp_stack(second.contiguous(), _block_specs(blocks[2:]), S, net.training)               # (P/S, 1024)
+    pooled = pooled.view(B, N // S, pooled.shape[1]).max(dim=1)[0]                                   # (B, 1024)
+    cat = torch.cat([second.view(B, N, -1), pooled.unsqueeze(1).expand(B, N, pooled.shape[1])], dim=2)
+    Cc = cat.shape[2]
+    if Cc % 4:
+        cat = F.pad(cat, (0, _r4(Cc) - Cc))
+    specs = _block_specs(list(net.seq_per_point2))
+    if net.output_size > 0:
+        specs.append(_LayerSpec(net.fc.weight, net.fc.bias, None, False))
+    out = mlp_stack(cat.reshape(P, cat.shape[2]), specs, 0, net.training)
+    out = from_channels_last(out.reshape(B, N, out.shape[1]))
+    if net.return_intermediate:
+        return out, pooled
+    return out

@@ -65,6 +65,9 @@ class MiniPointNet(nn.Module):
 
     def forward(self, x):
         """x (B,C,N) -> (B,output_size)."""
+        if runtime.fused_enabled() and x.is_cuda:
+            from ... import fused
+            return fused.minipointnet_forward(self, x)
         x = self.features(x)
         return self.fc(x) if self.output_size > 0 else x
 
@@ -92,6 +95,9 @@ class SegPointNet(nn.Module):
 
     def forward(self, x):
         """x (B,C,N) -> (B,output_size,N) [, intermediate features]."""
+        if runtime.fused_enabled() and x.is_cuda:
+            from ... import fused
+            return fused.segpointnet_forward(self, x)
         second = None
         for i, layer in enumerate(self.seq_per_point):
             x = layer(x)

@@ -42,7 +42,7 @@ class M2TRACK(base_model.MotionBaseModel):
 
     def _mlp(self, module, x):
         """(B,256) -> head output, on the fused kernels when enabled."""
-        if runtime.fused_enabled():
+        if runtime.fused_enabled() and x.is_cuda:
             from .. import fused
             return fused.rows_forward(module, x)
         return module(x)
