@@ -229,6 +229,14 @@ int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy, const floa
                     const float* in_scale, const float* in_shift, int in_relu, int P, int Cout, int Cin, float* dw,
                     int lddw, void* stream);
 
+/* wgrad, wide tiles (up to 256 x 256 of dW per CTA, all of TMEM), split over positions; the per-split partial tiles go
+ * to `part` (o3d_pw_wgrad_tc2_workspace_floats() floats) and a second kernel adds their sum into dw.              */
+long long o3d_pw_wgrad_tc2_workspace_floats(void);
+int o3d_pw_wgrad_tc2(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
+                     const float* dpool, const int32_t* sel, int S, int ldp, const float* x, int ldx,
+                     const float* in_scale, const float* in_shift, int in_relu, int P, int Cout, int Cin, float* dw,
+                     int lddw, float* part, long long part_floats, void* stream);
+
 /* Adam over a flat fp32 parameter bucket (torch.optim.Adam semantics; the reference uses betas (0.5, 0.999),
  * eps 1e-6: models/base_model.py:28-36).  state = device float[2] {step count (incremented by the call), lr}.  */
 int o3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float* state,

@@ -52,13 +52,17 @@ PROTOTYPES = {
     "o3d_pw_dgrad_tc": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _p, _p,
                         _p],
     "o3d_pw_wgrad_tc": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p],
+    "o3d_pw_wgrad_tc2_workspace_floats": [],
+    "o3d_pw_wgrad_tc2": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p,
+                         ctypes.c_longlong, _p],
     "o3d_adam_step": [_p, _p, _p, _p, ctypes.c_longlong, _p, _f, _f, _f, _f, _p],
     "o3d_stack_workspace_bytes": [_p, _i],
     "o3d_stack_forward": [_p, _p, _p, _p, _i, _p],
     "o3d_stack_backward": [_p, _p, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPE = {"o3d_last_error": ctypes.c_char_p, "o3d_pw_tc_wtile_bytes": ctypes.c_longlong,
-            "o3d_stack_workspace_bytes": ctypes.c_longlong, "o3d_debug_set": None}
+            "o3d_stack_workspace_bytes": ctypes.c_longlong, "o3d_debug_set": None,
+            "o3d_pw_wgrad_tc2_workspace_floats": ctypes.c_longlong}
 
 MAX_LAYERS = 8
 _I8, _F8, _P8 = ctypes.c_int * MAX_LAYERS, ctypes.c_float * MAX_LAYERS, ctypes.c_void_p * MAX_LAYERS

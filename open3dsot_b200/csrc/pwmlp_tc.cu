@@ -623,6 +623,212 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// wgrad, wide-tile variant: one CTA accumulates a (128*MH) x (128*NH) block of dW (MH*NH accumulators = up to all 512
+// TMEM columns) over its slice of positions, 16 positions per stage.  Relative to the 128x128 kernel above every loaded
+// activation row feeds twice as many MMAs, which halves the L2->SM traffic per FLOP — the limiter of that kernel — and
+// the split-K partial tiles are written with plain coalesced stores into a workspace and summed by a second kernel
+// instead of 65k float REDs per CTA.
+//   operand tile [16 positions x 128*H channels], MN-major SWIZZLE_128B_BASE32B: atom(cb, pq) at (cb + 4*H*pq) * 512
+//   descriptor (channel half h, k-step ks): start = tile + h*2048 + ks*2*SBO, LBO = 512, SBO = 4*H*512
+constexpr int WG2_K = 16;
+constexpr int WG2_STAGES = 3;
+constexpr int WG2_THREADS = 576;   // warps: 0 MMA | 1 prefetch | 2,3,12-17 producers | 4-11 epilogue
+
+template <int MH, int NH> struct Wg2Cfg {
+    static constexpr int A_BYTES = WG2_K * 128 * MH * 4;            // one of hi / lo
+    static constexpr int B_BYTES = WG2_K * 128 * NH * 4;
+    static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM = WG2_STAGES * STAGE + 1024 + 256;
+    static constexpr uint32_t TMEM = (MH * NH * 128) <= 128 ? 128 : ((MH * NH * 128) <= 256 ? 256 : 512);
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn2(uint32_t smem_addr, int H) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(512 >> 4) << 16;
+    d |= (uint64_t)((4 * H * 512) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+template <int H>
+__device__ __forceinline__ uint32_t sw_mn2(int p_local, int c4) {   // c4 = float4 index along the 128*H channels
+    const int cb = c4 >> 3, c32 = (c4 & 7) >> 1, half = c4 & 1, j0 = p_local & 3;
+    return (uint32_t)((cb + 4 * H * (p_local >> 2)) * 512 + j0 * 128 + ((c32 ^ j0) << 5) + (half << 4));
+}
+
+template <int MH, int NH>
+__global__ void __launch_bounds__(WG2_THREADS, 1)
+    pw_wgrad_tc2_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ part) {
+    using C = Wg2Cfg<MH, NH>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG2_STAGES * C::STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + WG2_STAGES;
+    uint64_t* tfull = bars + 2 * WG2_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG2_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.z * 128 * MH, n0 = blockIdx.y * 128 * NH;
+    const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
+    const int nkb = (pend - pbeg + WG2_K - 1) / WG2_K;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG2_STAGES; ++s) {
+            o3d_mbar_init(full + s, 256);
+            o3d_mbar_init(empty + s, 1);
+        }
+        o3d_mbar_init(tfull, 1);
+        o3d_fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, C::TMEM);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        const uint32_t idesc = make_idesc_mn(TC_M, TC_N);
+        int stage = 0, phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            o3d_mbar_wait(full + stage, phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sb = o3d_smem_u32(smem + stage * C::STAGE);
+                const uint32_t a_hi = sb, a_lo = sb + C::A_BYTES, b_hi = sb + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < WG2_K / 8; ++ks) {
+                    const uint32_t ao = ks * 2 * (4 * MH * 512), bo = ks * 2 * (4 * NH * 512);
+#pragma unroll
+                    for (int mh = 0; mh < MH; ++mh)
+#pragma unroll
+                        for (int nh = 0; nh < NH; ++nh) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((mh * NH + nh) * 128);
+                            const uint64_t ahi = make_desc_mn2(a_hi + mh * 2048 + ao, MH), alo = make_desc_mn2(a_lo + mh * 2048 + ao, MH);
+                            const uint64_t bhi = make_desc_mn2(b_hi + nh * 2048 + bo, NH), blo = make_desc_mn2(b_lo + nh * 2048 + bo, NH);
+                            umma_tf32(d_tmem, alo, bhi, idesc, (kb | ks) != 0);
+                            umma_tf32(d_tmem, ahi, blo, idesc, 1u);
+                            umma_tf32(d_tmem, ahi, bhi, idesc, 1u);
+                        }
+                }
+                umma_commit(empty + stage);
+                if (kb == nkb - 1) umma_commit(tfull);
+            }
+            __syncwarp();
+            if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int p = pbeg; p < pend; p += 512) {
+                da.prefetch_rows(p, 512, pend);
+                xb.prefetch_rows(p, 512, pend);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // epilogue: partial tile -> workspace part[split][m][n] (plain coalesced stores; zeros when this slice is empty)
+        const int q = warp & 3, grp = (warp - 4) >> 2;                 // grp 0: warps 4-7, 1: warps 8-11
+        const int Mt = 128 * MH * (int)gridDim.z, Nt = 128 * NH * (int)gridDim.y;
+        float* __restrict__ out = part + (size_t)blockIdx.x * Mt * Nt;
+        if (nkb > 0) {
+            o3d_mbar_wait(tfull, 0);
+            tc_fence_after();
+        }
+        for (int t = grp; t < MH * NH; t += 2) {                       // accumulators shared between the two warp groups
+            const int mh = t / NH, nh = t % NH;
+            const int row = m0 + mh * 128 + q * 32 + lane;
+            float* __restrict__ orow = out + (size_t)row * Nt + n0 + nh * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 128);
+#pragma unroll 1
+            for (int cg = 0; cg < 8; ++cg) {
+                uint32_t r[16];
+                if (nkb > 0) {
+                    tmem_ld16(taddr + cg * 16, r);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(orow + cg * 16 + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        }
+    } else {
+        // producers (8 warps): every thread serves both operands, raw loads first
+        const int pw = warp < 4 ? warp - 2 : warp - 10;
+        const int pt = pw * 32 + lane;                                  // 0..255
+        constexpr int CA = 32 * MH, CB = 32 * NH;                       // float4 per position row
+        constexpr int RA = WG2_K * CA / 256, RB = WG2_K * CB / 256;     // float4 per thread per stage (2 or 4)
+        const int ca4 = pt % CA, pa0 = pt / CA, sa = 256 / CA;          // A: rows pa0 + sa*i
+        const int cb4 = pt % CB, pb0 = pt / CB, sbs = 256 / CB;
+        const TcDy::Coef cfa = da.prep(m0 + ca4 * 4, M);
+        const TcAct::Coef cfb = xb.prep(n0 + cb4 * 4, N);
+        TcDy::Raw ra[RA];
+        TcAct::Raw rb[RB];
+        auto fetch = [&](int kb) {
+#pragma unroll
+            for (int i = 0; i < RA; ++i) ra[i] = da.fetch(pbeg + kb * WG2_K + pa0 + sa * i, pend, m0 + ca4 * 4, M);
+#pragma unroll
+            for (int i = 0; i < RB; ++i) rb[i] = xb.fetch(pbeg + kb * WG2_K + pb0 + sbs * i, pend, n0 + cb4 * 4, N);
+        };
+        int stage = 0, phase = 0;
+        if (nkb > 0) fetch(0);
+        for (int kb = 0; kb < nkb; ++kb) {
+            o3d_mbar_wait(empty + stage, phase ^ 1);
+            uint8_t* a_hi = smem + stage * C::STAGE;
+            uint8_t* a_lo = a_hi + C::A_BYTES;
+            uint8_t* b_hi = a_hi + 2 * C::A_BYTES;
+            uint8_t* b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+            for (int i = 0; i < RA; ++i) {
+                const int pl = pa0 + sa * i;
+                const float4 v = da.finish(ra[i], cfa, pbeg + kb * WG2_K + pl, pend);
+                const uint32_t off = sw_mn2<MH>(pl, ca4);
+                *reinterpret_cast<float4*>(a_hi + off) = hi_part(v);
+                *reinterpret_cast<float4*>(a_lo + off) = lo_part(v);
+            }
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                const int pl = pb0 + sbs * i;
+                const float4 v = xb.finish(rb[i], cfb, pbeg + kb * WG2_K + pl, pend);
+                const uint32_t off = sw_mn2<NH>(pl, cb4);
+                *reinterpret_cast<float4*>(b_hi + off) = hi_part(v);
+                *reinterpret_cast<float4*>(b_lo + off) = lo_part(v);
+            }
+            o3d_fence_proxy_async();
+            o3d_mbar_arrive(full + stage);
+            if (kb + 1 < nkb) fetch(kb + 1);
+            if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM);
+    }
+}
+
+// dW[m, n] (+)= sum over splits of part[s][m][n]   (Mt x Nt partial tiles -> the M x N corner of dW)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Mt, int Nt, int M, int N,
+                                    float* __restrict__ dW, int lddw) {
+    const int n4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, m = blockIdx.y;
+    if (n4 >= N || m >= M) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = part + (size_t)m * Nt + n4;
+    for (int s = 0; s < splits; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(p + (size_t)s * Mt * Nt);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* o = dW + (size_t)m * lddw + n4;
+    o[0] += acc.x;
+    if (n4 + 1 < N) o[1] += acc.y;
+    if (n4 + 2 < N) o[2] += acc.z;
+    if (n4 + 3 < N) o[3] += acc.w;
+}
+
 // Pre-tile a weight matrix W[rows, ld] (rows = UMMA M channels, k contiguous) into the per-(m_tile, k-block) shared-memory
 // images the kernel bulk-copies: [hi 16 KB | lo 16 KB], K-major SWIZZLE_128B, zero padded.
 __global__ void w_pretile_kernel(const float* __restrict__ W, int ld, int rows, int K, int nkb, uint8_t* __restrict__ out) {
@@ -738,4 +944,52 @@ extern "C" int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy,
     pw_wgrad_tc_kernel<<<dim3(splits, nt, mt), WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(da, xb, P, Cout, Cin, chunk, dw, lddw, g_tc_debug);
     O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc");
     return O3D_OK;
+}
+
+namespace {
+template <int MH, int NH>
+int launch_wgrad2(const TcDy& da, const TcAct& xb, int P, int Cout, int Cin, float* dw, int lddw, float* part,
+                  long long part_floats, cudaStream_t st) {
+    using C = Wg2Cfg<MH, NH>;
+    auto kern = pw_wgrad_tc2_kernel<MH, NH>;
+    O3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM), "o3d_pw_wgrad_tc2");
+    const int mt = (Cout + 128 * MH - 1) / (128 * MH), nt = (Cin + 128 * NH - 1) / (128 * NH);
+    const int Mt = mt * 128 * MH, Nt = nt * 128 * NH;
+    int splits = o3d_num_sms() / (mt * nt);
+    if (splits < 1) splits = 1;
+    const long long cap = part_floats / ((long long)Mt * Nt);
+    if (splits > cap) splits = (int)cap;
+    O3D_REQUIRE(splits >= 1, O3D_ERR_ARG, "o3d_pw_wgrad_tc2: workspace too small");
+    int chunk = (P + splits - 1) / splits;
+    chunk = ((chunk + WG2_K - 1) / WG2_K) * WG2_K;
+    splits = (P + chunk - 1) / chunk;
+    kern<<<dim3(splits, nt, mt), WG2_THREADS, C::SMEM, st>>>(da, xb, P, Cout, Cin, chunk, part);
+    O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc2");
+    dim3 rg((Cin / 4 + 63) / 64, Cout);
+    wgrad_reduce_kernel<<<rg, 64, 0, st>>>(part, splits, Mt, Nt, Cout, Cin, dw, lddw);
+    O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc2: reduce");
+    return O3D_OK;
+}
+}  // namespace
+
+extern "C" long long o3d_pw_wgrad_tc2_workspace_floats(void) {
+    return (long long)o3d_num_sms() * 256 * 256;   // splits * Mt * Nt never exceeds (#SMs / tiles) * tiles * 256 * 256
+}
+
+extern "C" int o3d_pw_wgrad_tc2(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
+                                const float* cc, const float* dpool, const int32_t* sel, int S, int ldp, const float* x,
+                                int ldx, const float* in_scale, const float* in_shift, int in_relu, int P, int Cout,
+                                int Cin, float* dw, int lddw, float* part, long long part_floats, void* stream) {
+    O3D_REQUIRE((g || dpool) && x && dw && part, O3D_ERR_ARG, "o3d_pw_wgrad_tc2: null pointer");
+    O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0 && (ldx & 3) == 0 && (lddw & 3) == 0, O3D_ERR_ARG,
+                "o3d_pw_wgrad_tc2: channel counts / leading dimensions must be multiples of 4");
+    if (P == 0) return O3D_OK;
+    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp};
+    TcAct xb{x, ldx, in_scale, in_shift, in_relu};
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool m2 = Cout > 128, n2 = Cin > 128;
+    if (m2 && n2) return launch_wgrad2<2, 2>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
+    if (m2) return launch_wgrad2<2, 1>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
+    if (n2) return launch_wgrad2<1, 2>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
+    return launch_wgrad2<1, 1>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
 }

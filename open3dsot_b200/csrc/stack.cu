@@ -77,7 +77,8 @@ struct Plan {
         stat[O3D_MAX_LAYERS], tiles[O3D_MAX_LAYERS];
     size_t ymax, ymin, arg, sel, ysel, stat_all, stat_bytes, fwd_bytes;
     // backward (temporary) offsets
-    size_t bstat, bstat_bytes, coef[O3D_MAX_LAYERS], dwp[O3D_MAX_LAYERS], btiles[O3D_MAX_LAYERS], dpool, gbuf[2], bwd_bytes;
+    size_t bstat, bstat_bytes, coef[O3D_MAX_LAYERS], dwp[O3D_MAX_LAYERS], btiles[O3D_MAX_LAYERS], dpool, gbuf[2], wpart, bwd_bytes;
+    long long wpart_floats;
 };
 
 bool make_plan(const o3d_stack_t* d, Plan& p) {
@@ -128,6 +129,12 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     if (maxn > maxk) maxk = maxn;
     p.dpool = o; o += p.S > 0 ? gsz : 0;
     for (int i = 0; i < 2; ++i) { p.gbuf[i] = o; o += al(sizeof(float) * (size_t)p.P * maxk); }
+    p.wpart = o;
+    p.wpart_floats = 0;
+    if ((d->use_tc & 2) && d->P >= 4096) {
+        p.wpart_floats = o3d_pw_wgrad_tc2_workspace_floats();
+        o += al(sizeof(float) * (size_t)p.wpart_floats);
+    }
     p.bwd_bytes = o;
     return true;
 }
@@ -294,8 +301,12 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
                 // tensor-core part: the first floor(K/128)*128 input channels; ragged tail (xyz / box-cloud extras)
                 // goes through the exact CUDA-core kernel on the remaining columns
                 const int Kmain = tc_main(K);
-                rc = o3d_pw_wgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, Kmain, dwp, K,
-                                     stream);
+                if ((d->use_tc & 4) == 0 && Nl % 128 == 0 && Kmain % 128 == 0 && (Nl >= 256 || Kmain >= 256))
+                    rc = o3d_pw_wgrad_tc2(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, Kmain, dwp,
+                                          K, at<float>(wb, p.wpart), p.wpart_floats, stream);
+                else
+                    rc = o3d_pw_wgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, Kmain, dwp,
+                                         K, stream);
                 if (rc) return rc;
                 if (K > Kmain)
                     rc = o3d_pw_wgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin + Kmain, K, psc ? psc + Kmain : nullptr,
