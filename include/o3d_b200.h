@@ -199,6 +199,7 @@ typedef struct o3d_stack_t {
     int use_tc;     /* allow the tcgen05 3xTF32 kernels where the shape qualifies                */
     int xyz_first;  /* layer-0 weight columns are [xyz(3) | features(c0)], input rows [features | dx dy dz 0] */
     int c0;         /* real feature channels of layer 0 when xyz_first                           */
+    int dx_cols;    /* backward: only the first dx_cols input columns need a gradient (0 = all K0) */
     int cin[O3D_MAX_LAYERS], cout[O3D_MAX_LAYERS], relu[O3D_MAX_LAYERS], has_bn[O3D_MAX_LAYERS];
     float momentum[O3D_MAX_LAYERS], eps[O3D_MAX_LAYERS];
     const float* weight[O3D_MAX_LAYERS];
@@ -219,7 +220,8 @@ long long o3d_stack_workspace_bytes(const o3d_stack_t* d, int backward);
 /* out: [P or P/S, round4(cout_last)]; ws_fwd must stay alive (untouched) until the backward call. */
 int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float* out, int keep_for_backward,
                       void* stream);
-/* dout: contiguous [rows, round4(cout_last)]; dx: [P, K0] or NULL. */
+/* dout: contiguous [rows, round4(cout_last)]; dx: [P, K0] or NULL (columns >= dx_cols are left undefined when
+ * dx_cols > 0). */
 int o3d_stack_backward(const o3d_stack_t* d, const float* x, const void* ws_fwd, void* ws_bwd, const float* out,
                        const float* dout, float* dx, void* stream);
 

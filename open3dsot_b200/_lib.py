@@ -71,7 +71,7 @@ _I8, _F8, _P8 = ctypes.c_int * MAX_LAYERS, ctypes.c_float * MAX_LAYERS, ctypes.c
 class StackDesc(ctypes.Structure):
     """ctypes mirror of `o3d_stack_t` (include/o3d_b200.h, block 4)."""
     _fields_ = [("n_layers", _i), ("P", _i), ("K0", _i), ("S", _i), ("training", _i), ("use_tc", _i),
-                ("xyz_first", _i), ("c0", _i),
+                ("xyz_first", _i), ("c0", _i), ("dx_cols", _i),
                 ("cin", _I8), ("cout", _I8), ("relu", _I8), ("has_bn", _I8),
                 ("momentum", _F8), ("eps", _F8),
                 ("weight", _P8), ("bias", _P8), ("gamma", _P8), ("beta", _P8),

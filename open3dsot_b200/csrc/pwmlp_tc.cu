@@ -812,21 +812,32 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
 }
 
 // dW[m, n] (+)= sum over splits of part[s][m][n]   (Mt x Nt partial tiles -> the M x N corner of dW)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Mt, int Nt, int M, int N,
-                                    float* __restrict__ dW, int lddw) {
-    const int n4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, m = blockIdx.y;
-    if (n4 >= N || m >= M) return;
+// 8 lanes share one float4 of output (each sums every 8th split, then a 3-step shuffle tree): 8x more loads in flight.
+__global__ void __launch_bounds__(256)
+    wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Mt, int Nt, int M, int N, float* __restrict__ dW,
+                        int lddw) {
+    const int sub = threadIdx.x & 7;
+    const int n4 = (blockIdx.x * 32 + (threadIdx.x >> 3)) * 4, m = blockIdx.y;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* p = part + (size_t)m * Nt + n4;
-    for (int s = 0; s < splits; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(p + (size_t)s * Mt * Nt);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (n4 < N && m < M) {
+        const float* p = part + (size_t)m * Nt + n4;
+        for (int s = sub; s < splits; s += 8) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)s * Mt * Nt));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
     }
-    float* o = dW + (size_t)m * lddw + n4;
-    o[0] += acc.x;
-    if (n4 + 1 < N) o[1] += acc.y;
-    if (n4 + 2 < N) o[2] += acc.z;
-    if (n4 + 3 < N) o[3] += acc.w;
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xFFFFFFFFu, acc.x, o); acc.y += __shfl_xor_sync(0xFFFFFFFFu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xFFFFFFFFu, acc.z, o); acc.w += __shfl_xor_sync(0xFFFFFFFFu, acc.w, o);
+    }
+    if (sub == 0 && n4 < N && m < M) {
+        float* o = dW + (size_t)m * lddw + n4;
+        o[0] += acc.x;
+        if (n4 + 1 < N) o[1] += acc.y;
+        if (n4 + 2 < N) o[2] += acc.z;
+        if (n4 + 3 < N) o[3] += acc.w;
+    }
 }
 
 // Pre-tile a weight matrix W[rows, ld] (rows = UMMA M channels, k contiguous) into the per-(m_tile, k-block) shared-memory
@@ -965,8 +976,8 @@ int launch_wgrad2(const TcDy& da, const TcAct& xb, int P, int Cout, int Cin, flo
     splits = (P + chunk - 1) / chunk;
     kern<<<dim3(splits, nt, mt), WG2_THREADS, C::SMEM, st>>>(da, xb, P, Cout, Cin, chunk, part);
     O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc2");
-    dim3 rg((Cin / 4 + 63) / 64, Cout);
-    wgrad_reduce_kernel<<<rg, 64, 0, st>>>(part, splits, Mt, Nt, Cout, Cin, dw, lddw);
+    dim3 rg((Cin / 4 + 31) / 32, Cout);
+    wgrad_reduce_kernel<<<rg, 256, 0, st>>>(part, splits, Mt, Nt, Cout, Cin, dw, lddw);
     O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc2: reduce");
     return O3D_OK;
 }

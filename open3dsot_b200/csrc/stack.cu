@@ -336,7 +336,9 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
                 rc = o3d_pw_dgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, tiles, p.P, Nl, Km, gout, K, yprev, K, psc, psh,
                                      prelu, ps1, ps2, stream);
                 if (rc) return rc;
-                if (K > Km)
+                // the ragged tail of a first layer holds (dx,dy,dz,0): skipped when the caller needs no coordinate gradient
+                const bool tail_wanted = !(l == 0 && d->dx_cols > 0 && d->dx_cols <= Km);
+                if (K > Km && tail_wanted)
                     rc = o3d_pw_dgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, at<float>(wf, p.wp[l]) + Km, K, p.P, Nl, K - Km,
                                       gout + Km, K, yprev ? yprev + Km : nullptr, K, psc ? psc + Km : nullptr,
                                       psh ? psh + Km : nullptr, prelu, ps1 ? ps1 + Km : nullptr, ps2 ? ps2 + Km : nullptr, stream);

@@ -78,7 +78,7 @@ def parse_stack(module):
 class _Meta:
     """Static description of one stack invocation (python objects only)."""
 
-    def __init__(self, specs, S, training, xyz_first=False, c0=0):
+    def __init__(self, specs, S, training, xyz_first=False, c0=0, dx_cols=0):
         if len(specs) > _lib.MAX_LAYERS:
             raise RuntimeError(f"fused MLP stack: at most {_lib.MAX_LAYERS} layers")
         self.n = len(specs)
@@ -86,6 +86,7 @@ class _Meta:
         self.training = bool(training)
         self.xyz_first = bool(xyz_first)
         self.c0 = int(c0)
+        self.dx_cols = int(dx_cols)
         self.bns = [s.bn for s in specs]
         self.relu = [bool(s.relu) for s in specs]
         self.cout = [s.weight.shape[0] for s in specs]
@@ -96,7 +97,7 @@ def _describe(meta, P, K0, params):
     d = _lib.StackDesc()
     d.n_layers, d.P, d.K0, d.S = meta.n, P, K0, meta.S
     d.training, d.use_tc = int(meta.training), int(runtime.tc_level())
-    d.xyz_first, d.c0 = int(meta.xyz_first), meta.c0
+    d.xyz_first, d.c0, d.dx_cols = int(meta.xyz_first), meta.c0, meta.dx_cols
     for l in range(meta.n):
         W, b, g, be = params[4 * l:4 * l + 4]
         bn = meta.bns[l]
@@ -169,19 +170,20 @@ class _MLPStackFn(torch.autograd.Function):
         return (None, dx, *grads)
 
 
-def mlp_stack(x2d, specs, S=0, training=True, xyz_first=False, c0=0):
+def mlp_stack(x2d, specs, S=0, training=True, xyz_first=False, c0=0, dx_cols=0):
     """Run a stack on a channels-last matrix.
 
     x2d        (P, K0) fp32, contiguous, K0 % 4 == 0 (zero-padded input channels)
     specs      list of _LayerSpec (parameters of the reference modules, checkpoint layout)
     S          pooling group size over consecutive positions (0 = dense output); must divide 128 and P
     xyz_first  layer-0 weight columns are [xyz(3) | features(c0)] while rows are [features | dx dy dz 0]
+    dx_cols    backward only needs the gradient of the first dx_cols input columns (0 = all)
     returns    (P or P//S, Cout_last)
     """
     if not x2d.is_cuda:
         raise RuntimeError("open3dsot_b200.fused: CUDA tensors required (there is no CPU path)")
     assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32 and x2d.shape[1] % 4 == 0
-    meta = _Meta(specs, S, training, xyz_first, c0)
+    meta = _Meta(specs, S, training, xyz_first, c0, dx_cols)
     params = []
     for s in specs:
         params += [s.weight, s.bias, s.bn.weight if s.bn is not None else None, s.bn.bias if s.bn is not None else None]
@@ -239,7 +241,11 @@ def sa_forward(sa, xyz, features, sample_idxs):
             raise RuntimeError("fused SA layer expects use_xyz=True (every shipped model does)")
         # the reference's channel order is [xyz(3), features(C)]; kernel rows are [features(Cp) | dx dy dz 0]:
         # the re-ordering of the first conv's columns happens inside o3d_stack_forward (xyz_first)
-        pooled = mlp_stack(grouped.view(B * npoint * S, Cp + 4), specs, S, sa.training, xyz_first=True, c0=C)
+        # coordinates that carry no gradient (every backbone layer; not the RPN's votes) spare the backward its
+        # (dx,dy,dz) columns
+        need_xyz = torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad)
+        pooled = mlp_stack(grouped.view(B * npoint * S, Cp + 4), specs, S, sa.training, xyz_first=True, c0=C,
+                           dx_cols=0 if (need_xyz or Cp == 0) else Cp)
         outs.append(from_channels_last(pooled.reshape(B, npoint, pooled.shape[1])))
     return new_xyz, outs
 
