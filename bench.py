@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--fused", type=int, default=None, help="override O3D_FUSED (1 = fused kernels, 0 = composed)")
     ap.add_argument("--tc", type=int, default=None, help="override O3D_TC (0 = CUDA cores, 1 = tcgen05 fwd+dgrad, 3 = + wgrad)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
+    ap.add_argument("--cfg", default=None, help="other config to exercise (P2B_Car.yaml, M2_track_kitti.yaml, ...): a parity / "
+                    "plumbing run of BASELINE.json configs[2..4], NOT the headline metric")
     return ap.parse_args()
 
 
@@ -253,7 +255,11 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
-    cfg = load_config(CFG_FILE, {"batch_size": args.batch})
+    cfg_file = CFG_FILE if args.cfg is None else os.path.join(ROOT, "cfgs", args.cfg)
+    cfg = load_config(cfg_file, {"batch_size": args.batch})
+    is_motion = cfg.net_model.lower() == "m2track"
+    if args.cfg is not None and "PEDESTRIAN_NUSCENES" in args.cfg:
+        cfg.template_size, cfg.search_size = 256, 512          # BASELINE.json configs[4] override
     torch.manual_seed(0)
     net = get_model(cfg.net_model)(cfg).to(dev).train()
     from open3dsot_b200.engine import TrainStep
@@ -261,8 +267,15 @@ def run_ours(args):
 
     # distinct host batches (pinned), one device-resident copy of each
     n_batches = 4
-    host = [synthetic_siamese_batch(args.batch, cfg.template_size, cfg.search_size, seed=20260924 + rank * 100 + i,
-                                    pin_memory=True) for i in range(n_batches)]
+    if is_motion:
+        from open3dsot_b200.datasets.synthetic import synthetic_motion_batch
+        host = [{k: v.pin_memory() for k, v in synthetic_motion_batch(args.batch, cfg.point_sample_size,
+                                                                      seed=20260924 + rank * 100 + i).items()}
+                for i in range(n_batches)]
+    else:
+        host = [synthetic_siamese_batch(args.batch, cfg.template_size, cfg.search_size, seed=20260924 + rank * 100 + i,
+                                        box_aware=getattr(cfg, "box_aware", False), pin_memory=True)
+                for i in range(n_batches)]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -352,10 +365,11 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(args.cpu_batch, args.cpu_steps)
     pairs = args.batch * world * args.steps
-    line = {"metric": METRIC, "value": pairs / (dev_ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+    workload = WORKLOAD if args.cfg is None else f"{args.cfg} train step, synthetic batch {args.batch}/GPU (not the headline config)"
+    line = {"metric": METRIC if args.cfg is None else "samples/sec, " + args.cfg, "value": pairs / (dev_ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+            "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                        "mode": "fused" if runtime.fused_enabled() else "composed",
                        "gemm_core": {0: "cuda-core-fp32", 1: "tcgen05-3xTF32 fwd+dgrad, cuda-core wgrad",
                                      3: "tcgen05-3xTF32 fwd+dgrad+wgrad"}.get(runtime.tc_level(), str(runtime.tc_level())),
