@@ -63,12 +63,22 @@ class TrainStep:
 
     def _capture(self, batch):
         self.static_batch = {k: v.clone() for k, v in batch.items()}
+        # settle allocator / lazy initialisation on a side stream, WITHOUT advancing training: parameters, optimizer
+        # state and BatchNorm buffers are snapshotted and restored around the two throw-away steps
+        buffers = list(self.model.buffers())
+        snap = (self.flat.flat.clone(), self.opt.exp_avg.clone(), self.opt.exp_avg_sq.clone(), self.opt.state.clone(),
+                [b.clone() for b in buffers])
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(2):                       # settle allocator / lazy initialisation on the capture stream
+            for _ in range(2):
                 self._eager(self.static_batch)
         torch.cuda.current_stream().wait_stream(s)
+        with torch.no_grad():
+            self.flat.flat.copy_(snap[0]); self.opt.exp_avg.copy_(snap[1]); self.opt.exp_avg_sq.copy_(snap[2])
+            self.opt.state.copy_(snap[3])
+            for b, old in zip(buffers, snap[4]):
+                b.copy_(old)
         # single rank: the whole step (incl. Adam) is one graph; multi-rank: forward+backward are captured and the
         # gradient all-reduce + Adam are enqueued right behind the replay (NCCL stays outside the capture)
         self.graph = torch.cuda.CUDAGraph()
