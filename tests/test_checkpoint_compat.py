@@ -1,0 +1,42 @@
+"""Drop-in check of the checkpoint surface: the reference's shipped BAT / M2-Track checkpoints
+load, key for key, into our modules.  Runs only where /root/reference exists (the authoring container)."""
+import os
+
+import pytest
+import torch
+
+from open3dsot_b200.checkpoint import load_lightning_checkpoint, load_reference_weights
+from open3dsot_b200.config import load_config
+from open3dsot_b200.models import get_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CKPT_DIR = "/root/reference/pretrained_models"
+pytestmark = pytest.mark.skipif(not os.path.isdir(CKPT_DIR), reason="reference checkpoints not present on this box")
+
+
+@pytest.mark.parametrize("ckpt,cfg_file", [("bat_kitti_car.ckpt", "BAT_Car.yaml"),
+                                           ("bat_kitti_pedestrian.ckpt", "BAT_Pedestrian.yaml"),
+                                           ("mmtrack_kitti_car.ckpt", "M2_track_kitti.yaml")])
+def test_reference_checkpoint_loads_strictly(ckpt, cfg_file):
+    cfg = load_config(os.path.join(ROOT, "cfgs", cfg_file))
+    net = get_model(cfg.net_model)(cfg)
+    ours = net.state_dict()
+    ck = load_reference_weights(net, os.path.join(CKPT_DIR, ckpt), strict=False)
+    ref_sd = ck["state_dict"]
+    # every parameter / buffer of ours exists in the checkpoint with the same shape; the checkpoint's extra entries are
+    # only the reference's metric-module buffers (torchmetrics), which carry no weights
+    for k, v in ours.items():
+        assert k in ref_sd and tuple(ref_sd[k].shape) == tuple(v.shape), k
+    extra = [k for k in ref_sd if k not in ours]
+    assert all(k.split(".")[0] in ("prec", "success", "seg_acc", "motion_acc") for k in extra), extra
+    assert "hyper_parameters" in ck and ck.get("pytorch-lightning_version", "").startswith("1.3")
+    w = net.state_dict()
+    some = next(k for k in w if k.endswith("weight") and w[k].dim() >= 2)
+    assert torch.equal(w[some], ref_sd[some])
+
+
+def test_checkpoint_hparams_are_attribute_accessible():
+    ck = load_lightning_checkpoint(os.path.join(CKPT_DIR, "bat_kitti_car.ckpt"))
+    hp = ck["hyper_parameters"]
+    cfg = hp["config"] if "config" in hp else hp
+    assert cfg.net_model == "BAT" and cfg.use_fps is True
