@@ -407,3 +407,29 @@ def segpointnet_forward(net, x):
     if net.return_intermediate:
         return out, pooled
     return out
+
+
+# ---------------------------------------------------------------------------------------------- FPS overlap
+_SIDE_STREAMS = {}
+
+
+def fps_ahead(points, npoint):
+    """Launch furthest-point sampling of `points` (B,N,3+) on a side stream and return (idx, join).  FPS is a serial chain
+    of npoint steps that occupies one CTA per cloud (48 of 148 SMs at config 2); started before the template branch it
+    runs underneath that branch's GEMMs.  `join()` makes the current stream wait for it (graph-capture safe fork/join)."""
+    cur = torch.cuda.current_stream()
+    dev = points.device.index
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=points.device)
+    xyz = points[..., 0:3].contiguous()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        idx = pointnet2_utils.furthest_point_sample(xyz, npoint)
+    xyz.record_stream(side)
+    idx.record_stream(cur)
+
+    def join():
+        cur.wait_stream(side)
+        return idx
+    return join

@@ -26,12 +26,14 @@ class Pointnet_Backbone(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
-    def forward(self, pointcloud, numpoints):
-        """pointcloud (B,N,3+C), numpoints [n1,n2,n3] -> xyz (B,n3,3), features (B,256,n3), SA1 sample idx (B,n1)."""
+    def forward(self, pointcloud, numpoints, first_sample_idxs=None):
+        """pointcloud (B,N,3+C), numpoints [n1,n2,n3] -> xyz (B,n3,3), features (B,256,n3), SA1 sample idx (B,n1).
+        `first_sample_idxs` (extension): SA1's FPS indices when they were computed ahead of time."""
         xyz, features = self._break_up_pc(pointcloud)
         l_xyz, l_features, l_idxs = [xyz], [features], []
         for i, sa in enumerate(self.SA_modules):
-            li_xyz, li_features, sample_idxs = sa(l_xyz[i], l_features[i], numpoints[i], True)
+            li_xyz, li_features, sample_idxs = sa(l_xyz[i], l_features[i], numpoints[i], True,
+                                                  sample_idxs=first_sample_idxs if i == 0 else None)
             l_xyz.append(li_xyz)
             l_features.append(li_features)
             l_idxs.append(sample_idxs)

@@ -47,8 +47,13 @@ class BAT(base_model.MatchingBaseModel):
         template, search = input_dict['template_points'], input_dict['search_points']
         template_bc = input_dict['points2cc_dist_t']
         M, N = template.shape[1], search.shape[1]
+        join = None
+        if self.config.use_fps and runtime.fused_enabled() and search.is_cuda:
+            from .. import fused
+            join = fused.fps_ahead(search, N // 2)           # search-branch FPS runs underneath the template branch
         template_xyz, template_feature, sample_idxs_t = self.backbone(template, [M // 2, M // 4, M // 8])
-        search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8])
+        search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8],
+                                                                first_sample_idxs=join() if join else None)
         template_feature = self._pointwise(self.conv_final, template_feature)
         search_feature = self._pointwise(self.conv_final, search_feature)
         pred_search_bc = self._pointwise(self.mlp_bc, torch.cat([search_xyz.transpose(1, 2), search_feature], dim=1))

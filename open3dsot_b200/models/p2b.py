@@ -30,8 +30,13 @@ class P2B(base_model.MatchingBaseModel):
         """input_dict: template_points (B,M,3), search_points (B,N,3) [+ labels]."""
         template, search = input_dict['template_points'], input_dict['search_points']
         M, N = template.shape[1], search.shape[1]
+        join = None
+        if self.config.use_fps and runtime.fused_enabled() and search.is_cuda:
+            from .. import fused
+            join = fused.fps_ahead(search, N // 2)
         template_xyz, template_feature, _ = self.backbone(template, [M // 2, M // 4, M // 8])
-        search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8])
+        search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8],
+                                                                first_sample_idxs=join() if join else None)
         template_feature = self._pointwise(self.conv_final, template_feature)
         search_feature = self._pointwise(self.conv_final, search_feature)
         fusion_feature = self.xcorr(template_feature, search_feature, template_xyz)

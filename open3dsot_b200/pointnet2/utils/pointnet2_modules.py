@@ -28,11 +28,14 @@ class _PointnetSAModuleBase(nn.Module):
         self.mlps = None
         self.use_fps = use_fps
 
-    def forward(self, xyz, features, npoint, return_idx=False):
+    def forward(self, xyz, features, npoint, return_idx=False, sample_idxs=None):
         """xyz (B,N,3), features (B,C,N)|None -> new_xyz (B,npoint,3), new_features (B,sum C_out,npoint)
-        [, sample_idxs (B,npoint) i32]."""
+        [, sample_idxs (B,npoint) i32].  `sample_idxs` (extension): centre indices computed ahead of time (e.g. FPS
+        overlapped with other work on a side stream); must equal what this layer would compute itself."""
         self.npoint = npoint
-        if self.use_fps:
+        if sample_idxs is not None:
+            pass
+        elif self.use_fps:
             sample_idxs = pointnet2_utils.furthest_point_sample(xyz, self.npoint)
         else:
             sample_idxs = torch.arange(self.npoint, dtype=torch.int32, device=xyz.device).repeat(xyz.size(0), 1)
