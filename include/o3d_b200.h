@@ -173,6 +173,7 @@ int o3d_dense_bwd_prep(const float* dout, int ldd, const float* out, int ldo, co
  * forward:  rows = Cout, K = Cin   (w = the padded conv weight)
  * dgrad  :  rows = Cin,  K = Cout  (w = its transpose)                                                */
 long long o3d_pw_tc_wtile_bytes(int rows, int K);
+void o3d_pw_tc_set_reverse(int rev);              /* next o3d_pw_*_tc launch of this thread walks the position tiles backwards */
 void o3d_debug_set(int tc_debug, int force_mt);   /* profiling experiments only (results invalid when non-zero) */
 int o3d_pw_tc_pretile(const float* w, int ldw, int rows, int K, void* wtiles, void* stream);
 int o3d_pw_fwd_tc(const float* x, int ldx, const float* in_scale, const float* in_shift, int in_relu, const void* wtiles,

@@ -298,7 +298,7 @@ constexpr int TC2_THREADS = 576;   // 18 warps: 0 MMA | 1 weights | 2,3,12-17 pr
 // 2 = producers skip the global loads, 4 = epilogue skips its global stores / loads
 template <int MT, class BLoad, class Epi>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
-    pw_tc_kernel(BLoad bl, const uint8_t* __restrict__ wtiles, int P, int K, int Nw, int nkb, Epi epi, int dbg) {
+    pw_tc_kernel(BLoad bl, const uint8_t* __restrict__ wtiles, int P, int K, int Nw, int nkb, Epi epi, int dbg, int rev) {
     using C = TcCfg<MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt0 = blockIdx.y * MT;              // first 128-channel tile of this CTA
     const int n_ptiles = (P + TC_N - 1) / TC_N;
+    // `rev`: walk the position tiles from the last to the first.  Consecutive layers alternate the direction, so a layer
+    // starts on the part of its input that the previous kernel touched last and that is still resident in the 126 MB L2.
+    auto tile_of = [&](int t) { return rev ? n_ptiles - 1 - t : t; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -367,9 +370,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         // ===================================================== weight-tile streamer (bulk copy engine)
         if (lane == 0) {
             int stage = 0, phase = 0;
-            if (!(dbg & 8)) bl.prefetch_rows(blockIdx.x * TC_N, TC_N, P);
+            if (!(dbg & 8) && (int)blockIdx.x < n_ptiles) bl.prefetch_rows(tile_of(blockIdx.x) * TC_N, TC_N, P);
             for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
-                if (!(dbg & 8)) bl.prefetch_rows((t + (int)gridDim.x) * TC_N, TC_N, P);   // next tile of this CTA -> L2
+                if (!(dbg & 8) && t + (int)gridDim.x < n_ptiles)
+                    bl.prefetch_rows(tile_of(t + (int)gridDim.x) * TC_N, TC_N, P);   // next tile of this CTA -> L2
                 for (int kb = 0; kb < nkb; ++kb) {
                     o3d_mbar_wait(empty + stage, phase ^ 1);
                     if ((dbg & 1) && t != (int)blockIdx.x) {
@@ -396,7 +400,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         const int Nw_e = (dbg & 4) ? 0 : Nw;          // dbg: ch >= Nw_e -> the epilogue body is skipped
         int acc = 0, aphase = 0;
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
-            epi.prefetch(ch, Nw_e, t * TC_N + cg0 * 16, P);
+            const int pt0 = tile_of(t) * TC_N;
+            epi.prefetch(ch, Nw_e, pt0 + cg0 * 16, P);
             o3d_mbar_wait(tfull + acc, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + m) * TC_N);
@@ -404,8 +409,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
             for (int cg = cg0; cg < cg1; ++cg) {
                 uint32_t r[16];
                 tmem_ld16(taddr + cg * 16, r);
-                epi.group(r, ch, Nw_e, t * TC_N + cg * 16, P);
-                if (cg + 1 < cg1) epi.prefetch(ch, Nw_e, t * TC_N + (cg + 1) * 16, P);
+                epi.group(r, ch, Nw_e, pt0 + cg * 16, P);
+                if (cg + 1 < cg1) epi.prefetch(ch, Nw_e, pt0 + (cg + 1) * 16, P);
             }
             tc_fence_before();
             o3d_mbar_arrive(tempty + acc);
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         int stage = 0, phase = 0;
         if (dbg & 2) P = 0;                               // dbg: nothing is loaded
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
-            const int p0 = t * TC_N;
+            const int p0 = tile_of(t) * TC_N;
             typename BLoad::Raw raw[4];
             typename BLoad::Coef cf = bl.prep(chunk * 4, K);
             if (P > 0) {
@@ -496,9 +501,9 @@ __device__ __forceinline__ uint32_t sw128_mn(int p_local, int c4) {   // c4 = fl
 
 // One operand's producer loop of the wgrad kernel: raw loads of k-block kb+1 are issued right after k-block kb has been
 // handed to the tensor core; transform + hi/lo split happen at store time.
-template <class L>
+template <class L, class KPos>
 __device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int tile_off, uint64_t* full, uint64_t* empty,
-                                              int pt, int c_base, int CH, int pbeg, int pend, int nkb) {
+                                              int pt, int c_base, int CH, KPos kpos, int pend, int nkb) {
     const int c4 = pt & 31, prow0 = pt >> 5;      // rows prow0 + 4*i
     const int ch0 = c_base + c4 * 4;
     const typename L::Coef cf = ld.prep(ch0, CH);
@@ -506,7 +511,7 @@ __device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int ti
     int stage = 0, phase = 0;
     if (nkb > 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) raw[i] = ld.fetch(pbeg + prow0 + 4 * i, pend, ch0, CH);
+        for (int i = 0; i < 8; ++i) raw[i] = ld.fetch(kpos(0) + prow0 + 4 * i, pend, ch0, CH);
     }
     for (int kb = 0; kb < nkb; ++kb) {
         o3d_mbar_wait(empty + stage, phase ^ 1);
@@ -514,7 +519,7 @@ __device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int ti
         uint8_t* lo = hi + TILE_BYTES;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 v = ld.finish(raw[i], cf, pbeg + kb * TC_K + prow0 + 4 * i, pend);
+            const float4 v = ld.finish(raw[i], cf, kpos(kb) + prow0 + 4 * i, pend);
             const uint32_t off = sw128_mn(prow0 + 4 * i, c4);
             *reinterpret_cast<float4*>(hi + off) = hi_part(v);
             *reinterpret_cast<float4*>(lo + off) = lo_part(v);
@@ -523,7 +528,7 @@ __device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int ti
         o3d_mbar_arrive(full + stage);
         if (kb + 1 < nkb) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) raw[i] = ld.fetch(pbeg + (kb + 1) * TC_K + prow0 + 4 * i, pend, ch0, CH);
+            for (int i = 0; i < 8; ++i) raw[i] = ld.fetch(kpos(kb + 1) + prow0 + 4 * i, pend, ch0, CH);
         }
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
     }
@@ -541,8 +546,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.z * TC_M, n0 = blockIdx.y * TC_N;
+    // every split owns one contiguous slice of positions (DRAM-friendly; a round-robin deal of k-blocks measured slower)
     const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
-    const int nkb = (pend - pbeg + TC_K - 1) / TC_K;
+    const int nkb = pend > pbeg ? (pend - pbeg + TC_K - 1) / TC_K : 0;
+    auto kpos = [&](int i) { return pbeg + i * TC_K; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -612,8 +619,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     } else if (warp >= 8) {
         // producers: warps 8-11 -> A (dY, channels m0..), warps 12-15 -> B (X, channels n0..)
         const int pt = (threadIdx.x - 256) & 127;
-        if (warp < 12) wgrad_produce(da, smem, 0, full, empty, pt, m0, M, pbeg, pend, nkb);
-        else wgrad_produce(xb, smem, 2 * TILE_BYTES, full, empty, pt, n0, N, pbeg, pend, nkb);
+        if (warp < 12) wgrad_produce(da, smem, 0, full, empty, pt, m0, M, kpos, pend, nkb);
+        else wgrad_produce(xb, smem, 2 * TILE_BYTES, full, empty, pt, n0, N, kpos, pend, nkb);
     }
     tc_fence_before();
     __syncthreads();
@@ -673,7 +680,8 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.z * 128 * MH, n0 = blockIdx.y * 128 * NH;
     const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
-    const int nkb = (pend - pbeg + WG2_K - 1) / WG2_K;
+    const int nkb = pend > pbeg ? (pend - pbeg + WG2_K - 1) / WG2_K : 0;
+    auto kpos = [&](int i) { return pbeg + i * WG2_K; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WG2_STAGES; ++s) {
@@ -769,9 +777,9 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
         TcAct::Raw rb[RB];
         auto fetch = [&](int kb) {
 #pragma unroll
-            for (int i = 0; i < RA; ++i) ra[i] = da.fetch(pbeg + kb * WG2_K + pa0 + sa * i, pend, m0 + ca4 * 4, M);
+            for (int i = 0; i < RA; ++i) ra[i] = da.fetch(kpos(kb) + pa0 + sa * i, pend, m0 + ca4 * 4, M);
 #pragma unroll
-            for (int i = 0; i < RB; ++i) rb[i] = xb.fetch(pbeg + kb * WG2_K + pb0 + sbs * i, pend, n0 + cb4 * 4, N);
+            for (int i = 0; i < RB; ++i) rb[i] = xb.fetch(kpos(kb) + pb0 + sbs * i, pend, n0 + cb4 * 4, N);
         };
         int stage = 0, phase = 0;
         if (nkb > 0) fetch(0);
@@ -784,7 +792,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < RA; ++i) {
                 const int pl = pa0 + sa * i;
-                const float4 v = da.finish(ra[i], cfa, pbeg + kb * WG2_K + pl, pend);
+                const float4 v = da.finish(ra[i], cfa, kpos(kb) + pl, pend);
                 const uint32_t off = sw_mn2<MH>(pl, ca4);
                 *reinterpret_cast<float4*>(a_hi + off) = hi_part(v);
                 *reinterpret_cast<float4*>(a_lo + off) = lo_part(v);
@@ -792,7 +800,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
                 const int pl = pb0 + sbs * i;
-                const float4 v = xb.finish(rb[i], cfb, pbeg + kb * WG2_K + pl, pend);
+                const float4 v = xb.finish(rb[i], cfb, kpos(kb) + pl, pend);
                 const uint32_t off = sw_mn2<NH>(pl, cb4);
                 *reinterpret_cast<float4*>(b_hi + off) = hi_part(v);
                 *reinterpret_cast<float4*>(b_lo + off) = lo_part(v);
@@ -857,6 +865,7 @@ __global__ void w_pretile_kernel(const float* __restrict__ W, int ld, int rows, 
 }
 
 int g_tc_debug = 0, g_tc_force_mt = 0;
+thread_local int g_tc_rev = 0;   // direction of the next launch (set by the stack sequencer)
 
 template <int MT, class BLoad, class Epi>
 int launch_tc_mt(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cudaStream_t st, const char* name) {
@@ -869,7 +878,7 @@ int launch_tc_mt(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi,
     int gx = o3d_num_sms() / gy;
     if (gx < 1) gx = 1;
     if (gx > n_ptiles) gx = n_ptiles;
-    kern<<<dim3(gx, gy), TC2_THREADS, TcCfg<MT>::SMEM, st>>>(bl, wtiles, P, K, Nw, nkb, epi, g_tc_debug);
+    kern<<<dim3(gx, gy), TC2_THREADS, TcCfg<MT>::SMEM, st>>>(bl, wtiles, P, K, Nw, nkb, epi, g_tc_debug, g_tc_rev);
     O3D_CHECK_LAUNCH(name);
     return O3D_OK;
 }
@@ -885,6 +894,7 @@ int launch_tc(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cu
 }  // namespace
 
 extern "C" void o3d_debug_set(int tc_debug, int force_mt) { g_tc_debug = tc_debug; g_tc_force_mt = force_mt; }
+extern "C" void o3d_pw_tc_set_reverse(int rev) { g_tc_rev = rev; }
 
 extern "C" long long o3d_pw_tc_wtile_bytes(int rows, int K) {
     const long long mt = (rows + TC_M - 1) / TC_M, nkb = (K + TC_K - 1) / TC_K;

@@ -189,6 +189,8 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
         int32_t* arg = pool ? at<int32_t>(ws, p.arg) : nullptr;
         int rc;
         if (p.tc_f[l]) {
+            // snake order: layer 0 starts where the grouping kernel finished (the end), layer 1 where layer 0 finished, ...
+            o3d_pw_tc_set_reverse((l & 1) == 0);
             void* tiles = ws + p.tiles[l];
             rc = o3d_pw_tc_pretile(wp, K, Nw, K, tiles, stream);
             if (rc) return rc;
@@ -293,6 +295,38 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         const float* psc = (l > 0 && d->has_bn[l - 1]) ? pvec : nullptr;
         const float* psh = (l > 0 && d->has_bn[l - 1]) ? pvec + Kp : nullptr;
         const int prelu = l > 0 ? d->relu[l - 1] : 0;
+        if (l > 0 || dx) {
+            float* gout = l > 0 ? at<float>(wb, p.gbuf[gsel]) : dx;
+            const bool mask = l > 0 && (d->has_bn[l - 1] || d->relu[l - 1]);
+            const bool want = l > 0 && (d->has_bn[l - 1] || d->bias[l - 1] != nullptr);
+            const float* yprev = mask ? at<float>(wf, p.y[l - 1]) : nullptr;
+            double* ps1 = want ? s1(l - 1) : nullptr;
+            double* ps2 = want ? s1(l - 1) + K : nullptr;
+            if (p.tc_b[l]) {
+                o3d_pw_tc_set_reverse(0);   // dgrad sweeps forward; the wgrad that follows sweeps the same rows backward
+                // tensor cores on the first floor(K/128)*128 input channels, exact CUDA-core kernel on the ragged tail
+                // (the xyz / box-cloud extras of a first layer)
+                const int Km = tc_main(K);
+                void* tiles = wb + p.btiles[l];
+                rc = o3d_pw_tc_pretile(at<float>(wf, p.wt[l]), Nl, Km, Nl, tiles, stream);
+                if (rc) return rc;
+                rc = o3d_pw_dgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, tiles, p.P, Nl, Km, gout, K, yprev, K, psc, psh,
+                                     prelu, ps1, ps2, stream);
+                if (rc) return rc;
+                // the ragged tail of a first layer holds (dx,dy,dz,0): skipped when the caller needs no coordinate gradient
+                const bool tail_wanted = !(l == 0 && d->dx_cols > 0 && d->dx_cols <= Km);
+                if (K > Km && tail_wanted)
+                    rc = o3d_pw_dgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, at<float>(wf, p.wp[l]) + Km, K, p.P, Nl, K - Km,
+                                      gout + Km, K, yprev ? yprev + Km : nullptr, K, psc ? psc + Km : nullptr,
+                                      psh ? psh + Km : nullptr, prelu, ps1 ? ps1 + Km : nullptr, ps2 ? ps2 + Km : nullptr, stream);
+            } else {
+                rc = o3d_pw_dgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, at<float>(wf, p.wp[l]), K, p.P, Nl, K, gout, K,
+                                  yprev, K, psc, psh, prelu, ps1, ps2, stream);
+            }
+            if (rc) return rc;
+            g = gout;
+            gsel ^= 1;
+        }
         if (d->d_weight[l]) {
             float* dwp = at<float>(wb, p.dwp[l]);
             O3D_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)Nl * K, st), "o3d_stack_backward: memset dW");
@@ -318,37 +352,6 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
             unpack_wgrad_kernel<<<(cout * K + 255) / 256, 256, 0, st>>>(dwp, cout, d->cin[l], K, l == 0 ? d->xyz_first : 0,
                                                                         d->c0, d->d_weight[l]);
             O3D_CHECK_LAUNCH("o3d_stack_backward: unpack_wgrad");
-        }
-        if (l > 0 || dx) {
-            float* gout = l > 0 ? at<float>(wb, p.gbuf[gsel]) : dx;
-            const bool mask = l > 0 && (d->has_bn[l - 1] || d->relu[l - 1]);
-            const bool want = l > 0 && (d->has_bn[l - 1] || d->bias[l - 1] != nullptr);
-            const float* yprev = mask ? at<float>(wf, p.y[l - 1]) : nullptr;
-            double* ps1 = want ? s1(l - 1) : nullptr;
-            double* ps2 = want ? s1(l - 1) + K : nullptr;
-            if (p.tc_b[l]) {
-                // tensor cores on the first floor(K/128)*128 input channels, exact CUDA-core kernel on the ragged tail
-                // (the xyz / box-cloud extras of a first layer)
-                const int Km = tc_main(K);
-                void* tiles = wb + p.btiles[l];
-                rc = o3d_pw_tc_pretile(at<float>(wf, p.wt[l]), Nl, Km, Nl, tiles, stream);
-                if (rc) return rc;
-                rc = o3d_pw_dgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, tiles, p.P, Nl, Km, gout, K, yprev, K, psc, psh,
-                                     prelu, ps1, ps2, stream);
-                if (rc) return rc;
-                // the ragged tail of a first layer holds (dx,dy,dz,0): skipped when the caller needs no coordinate gradient
-                const bool tail_wanted = !(l == 0 && d->dx_cols > 0 && d->dx_cols <= Km);
-                if (K > Km && tail_wanted)
-                    rc = o3d_pw_dgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, at<float>(wf, p.wp[l]) + Km, K, p.P, Nl, K - Km,
-                                      gout + Km, K, yprev ? yprev + Km : nullptr, K, psc ? psc + Km : nullptr,
-                                      psh ? psh + Km : nullptr, prelu, ps1 ? ps1 + Km : nullptr, ps2 ? ps2 + Km : nullptr, stream);
-            } else {
-                rc = o3d_pw_dgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, at<float>(wf, p.wp[l]), K, p.P, Nl, K, gout, K,
-                                  yprev, K, psc, psh, prelu, ps1, ps2, stream);
-            }
-            if (rc) return rc;
-            g = gout;
-            gsel ^= 1;
         }
     }
     return O3D_OK;
