@@ -29,18 +29,59 @@ __device__ __forceinline__ int src_col(int k, int K, int cin, int xyz_first, int
     return -1;
 }
 
+// One kernel prepares everything a layer's GEMMs need from the checkpoint-layout weight:
+//   wp [Nw, K] zero-padded (+ column re-ordering), wt [K, Nw] its transpose, the zero-padded bias, and — when the tensor-core
+//   kernels take the layer — the pre-tiled hi|lo shared-memory images for the forward GEMM (rows = output channels) and
+//   for the dgrad GEMM (rows = input channels); the image layout is the one documented at w_pretile_kernel (pwmlp_tc.cu).
+// A thread owns 4 consecutive k of one (padded) row n.
+__device__ __forceinline__ uint32_t tile_sw128(int r, int c) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 __global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int cin, int Nw, int K, int xyz_first, int c0,
-                                   float* __restrict__ wp, float* __restrict__ wt) {
+                                   float* __restrict__ wp, float* __restrict__ wt, const float* __restrict__ bias,
+                                   float* __restrict__ bias_p, uint8_t* __restrict__ tiles_f, uint8_t* __restrict__ tiles_b,
+                                   int Km /* input channels tiled for dgrad */, int Npad, int Kpad /* iteration space */) {
+    constexpr int TILE = 128 * 32 * 4;
+    const int nkb_f = (K + 31) / 32;
+    const int k4n = Kpad / 4;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Nw * K) return;
-    const int n = i / K, k = i % K;
-    float v = 0.f;
+    if (bias_p && i < Nw) bias_p[i] = i < cout ? bias[i] : 0.f;
+    if (i >= Npad * k4n) return;
+    const int n = i / k4n, k = (i % k4n) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (n < cout) {
-        const int sc = src_col(k, K, cin, xyz_first, c0);
-        if (sc >= 0) v = src[(size_t)n * cin + sc];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int sc = (k + j < K) ? src_col(k + j, K, cin, xyz_first, c0) : -1;
+            if (sc >= 0) v[j] = src[(size_t)n * cin + sc];
+        }
     }
-    wp[i] = v;
-    wt[(size_t)k * Nw + n] = v;
+    if (n < Nw && k < K) {
+        *reinterpret_cast<float4*>(wp + (size_t)n * K + k) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wt[(size_t)(k + j) * Nw + n] = v[j];
+    }
+    if (tiles_f && k < nkb_f * 32) {   // forward image: tile (n / 128, k / 32), row n % 128, 16-byte chunk (k % 32) / 4
+        uint8_t* dst = tiles_f + ((size_t)(n >> 7) * nkb_f + (k >> 5)) * (2 * TILE) + tile_sw128(n & 127, (k & 31) >> 2);
+        *reinterpret_cast<float4*>(dst) = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
+        *reinterpret_cast<float4*>(dst + TILE) =
+            make_float4(v[0] - tf32_hi(v[0]), v[1] - tf32_hi(v[1]), v[2] - tf32_hi(v[2]), v[3] - tf32_hi(v[3]));
+    }
+    if (tiles_b && n < ((Nw + 31) / 32) * 32) {   // dgrad image: rows = input channels k..k+3 (< Km), "K" index = n
+        const int nkb_b = (Nw + 31) / 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = k + j;
+            if (row >= ((Km + 127) / 128) * 128) continue;
+            const float val = row < Km ? v[j] : 0.f;
+            uint8_t* dst = tiles_b + ((size_t)(row >> 7) * nkb_b + (n >> 5)) * (2 * TILE) + tile_sw128(row & 127, (n & 31) >> 2) +
+                           (n & 3) * 4;
+            *reinterpret_cast<float*>(dst) = tf32_hi(val);
+            *reinterpret_cast<float*>(dst + TILE) = val - tf32_hi(val);
+        }
+    }
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int cout, int cin, int K, int xyz_first, int c0,
@@ -52,19 +93,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int cout, int
     if (sc >= 0) dst[(size_t)n * cin + sc] = dwp[i];
 }
 
-__global__ void pad_vec_kernel(const float* __restrict__ src, int n, int npad, float* __restrict__ dst) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < npad) dst[i] = i < n ? src[i] : 0.f;
-}
-
 __global__ void d2f_kernel(const double* __restrict__ src, int n, float* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (float)src[i];
-}
-
-__global__ void copy_f_kernel(const float* __restrict__ src, int n, float* __restrict__ dst) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
 }
 
 // ---- workspace plan -------------------------------------------------------------------------------------------
@@ -96,13 +127,14 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     // statistics block first (one memset)
     p.stat_all = o;
     for (int l = 0; l < p.n; ++l) { p.stat[l] = o; o += al(sizeof(double) * 2 * p.Nw[l]); }
+    for (int l = 0; l < p.n; ++l) { p.vec[l] = o; o += al(sizeof(float) * 4 * p.Nw[l]); }   // zeroed together with the stats
     p.stat_bytes = o - p.stat_all;
     for (int l = 0; l < p.n; ++l) {
         p.wp[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]);
         p.wt[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]);
         p.bias[l] = o; o += al(sizeof(float) * p.Nw[l]);
-        p.vec[l] = o; o += al(sizeof(float) * 4 * p.Nw[l]);
         p.tiles[l] = o; if (p.tc_f[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(p.Nw[l], p.K[l]));
+        p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(tc_main(p.K[l]), p.Nw[l]));
         p.y[l] = o; o += al(sizeof(float) * (size_t)p.P * p.Nw[l]);
     }
     const size_t gsz = al(sizeof(float) * (size_t)p.rows * p.Nw[p.n - 1]);
@@ -116,12 +148,11 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     o = 0;
     p.bstat = o;
     for (int l = 0; l < p.n; ++l) o += al(sizeof(double) * 2 * p.Nw[l]);
-    p.bstat_bytes = o;
     size_t maxk = 0;
+    for (int l = 0; l < p.n; ++l) { p.coef[l] = o; o += al(sizeof(float) * 5 * p.Nw[l]); }
+    for (int l = 0; l < p.n; ++l) { p.dwp[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]); }
+    p.bstat_bytes = o;                      // sums | BN-backward coefficients | padded weight gradients: one memset
     for (int l = 0; l < p.n; ++l) {
-        p.coef[l] = o; o += al(sizeof(float) * 5 * p.Nw[l]);
-        p.dwp[l] = o; o += al(sizeof(float) * (size_t)p.Nw[l] * p.K[l]);
-        p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(tc_main(p.K[l]), p.Nw[l]));
         if ((size_t)p.K[l] > maxk) maxk = p.K[l];
     }
     size_t maxn = 0;
@@ -160,7 +191,7 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
     if (p.P == 0) return O3D_OK;
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* ws = (uint8_t*)ws_fwd;
-    if (d->training) O3D_CUDA(cudaMemsetAsync(ws + p.stat_all, 0, p.stat_bytes, st), "o3d_stack_forward: memset");
+    O3D_CUDA(cudaMemsetAsync(ws + p.stat_all, 0, p.stat_bytes, st), "o3d_stack_forward: memset");   // statistics + BN vectors
     const float* cur = x;
     int cur_ld = d->K0;
     const float *in_scale = nullptr, *in_shift = nullptr;
@@ -170,14 +201,23 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
         const int Nw = p.Nw[l], K = p.K[l], cout = d->cout[l];
         float* wp = at<float>(ws, p.wp[l]);
         float* wt = at<float>(ws, p.wt[l]);
-        pack_weight_kernel<<<(Nw * K + 255) / 256, 256, 0, st>>>(d->weight[l], cout, d->cin[l], Nw, K,
-                                                                 l == 0 ? d->xyz_first : 0, d->c0, wp, wt);
-        O3D_CHECK_LAUNCH("o3d_stack_forward: pack_weight");
-        float* bias = nullptr;
-        if (d->bias[l]) {
-            bias = at<float>(ws, p.bias[l]);
-            pad_vec_kernel<<<(Nw + 127) / 128, 128, 0, st>>>(d->bias[l], cout, Nw, bias);
+        float* bias = d->bias[l] ? at<float>(ws, p.bias[l]) : nullptr;
+        {
+            uint8_t* tf = p.tc_f[l] ? ws + p.tiles[l] : nullptr;
+            uint8_t* tb = (p.tc_b[l] && keep_for_backward) ? ws + p.btiles[l] : nullptr;
+            const int Km = tc_main(K);
+            int Npad = Nw, Kpad = K;
+            if (tf) { Npad = ((Nw + 127) / 128) * 128; Kpad = ((K + 31) / 32) * 32; }
+            if (tb) {
+                if (Npad < ((Nw + 31) / 32) * 32) Npad = ((Nw + 31) / 32) * 32;
+                if (Kpad < ((Km + 127) / 128) * 128) Kpad = ((Km + 127) / 128) * 128;
+            }
+            const int work = Npad * (Kpad / 4);
+            pack_weight_kernel<<<(work + 255) / 256, 256, 0, st>>>(d->weight[l], cout, d->cin[l], Nw, K,
+                                                                   l == 0 ? d->xyz_first : 0, d->c0, wp, wt, d->bias[l], bias,
+                                                                   tf, tb, Km, Npad, Kpad);
         }
+        O3D_CHECK_LAUNCH("o3d_stack_forward: pack_weight");
         const bool last = l == L, pool = last && p.S > 0;
         const bool keep_y = !last || keep_for_backward || !pool;
         float* y = keep_y ? at<float>(ws, p.y[l]) : nullptr;
@@ -192,8 +232,6 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
             // snake order: layer 0 starts where the grouping kernel finished (the end), layer 1 where layer 0 finished, ...
             o3d_pw_tc_set_reverse((l & 1) == 0);
             void* tiles = ws + p.tiles[l];
-            rc = o3d_pw_tc_pretile(wp, K, Nw, K, tiles, stream);
-            if (rc) return rc;
             rc = o3d_pw_fwd_tc(cur, cur_ld, in_scale, in_shift, in_relu, tiles, bias, p.P, K, cout, y, Nw, sum, sumsq,
                                pool ? p.S : 0, ymax, ymin, arg, Nw, stream);
         } else {
@@ -205,7 +243,6 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
         float *sc = nullptr, *sh = nullptr;
         if (d->has_bn[l]) {
             sc = vec; sh = vec + Nw;
-            O3D_CUDA(cudaMemsetAsync(vec, 0, sizeof(float) * 4 * Nw, st), "o3d_stack_forward: memset vec");
             rc = o3d_bn_fwd_finalize(sum, sumsq, (double)p.P, d->gamma[l], d->beta[l], d->running_mean[l], d->running_var[l],
                                      d->training ? d->num_batches_tracked[l] : nullptr, d->momentum[l], d->eps[l],
                                      d->training, cout, sc, sh, vec + 2 * Nw, vec + 3 * Nw, stream);
@@ -271,13 +308,10 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         const float *a = nullptr, *b = nullptr, *cc = nullptr;
         const float* vec = at<float>(wf, p.vec[l]);
         if (d->has_bn[l]) {
-            O3D_CUDA(cudaMemsetAsync(coef, 0, sizeof(float) * 5 * Nl, st), "o3d_stack_backward: memset coef");
             rc = o3d_bn_bwd_finalize(s1(l), s1(l) + Nl, (double)p.P, d->gamma[l], vec + 2 * Nl, vec + 3 * Nl, d->training,
-                                     cout, coef, coef + Nl, coef + 2 * Nl, coef + 3 * Nl, coef + 4 * Nl, stream);
+                                     cout, coef, coef + Nl, coef + 2 * Nl, d->d_gamma[l], d->d_beta[l], stream);
             if (rc) return rc;
             a = coef; b = coef + Nl; cc = coef + 2 * Nl;
-            if (d->d_gamma[l]) copy_f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(coef + 3 * Nl, cout, d->d_gamma[l]);
-            if (d->d_beta[l]) copy_f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(coef + 4 * Nl, cout, d->d_beta[l]);
             if (d->d_bias[l]) O3D_CUDA(cudaMemsetAsync(d->d_bias[l], 0, sizeof(float) * cout, st), "d_bias");  // BN removes the mean
         } else if (d->d_bias[l]) {
             d2f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(s1(l), cout, d->d_bias[l]);
@@ -307,9 +341,7 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
                 // tensor cores on the first floor(K/128)*128 input channels, exact CUDA-core kernel on the ragged tail
                 // (the xyz / box-cloud extras of a first layer)
                 const int Km = tc_main(K);
-                void* tiles = wb + p.btiles[l];
-                rc = o3d_pw_tc_pretile(at<float>(wf, p.wt[l]), Nl, Km, Nl, tiles, stream);
-                if (rc) return rc;
+                const void* tiles = wf + p.btiles[l];   // written by the forward pass's pack kernel
                 rc = o3d_pw_dgrad_tc(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, tiles, p.P, Nl, Km, gout, K, yprev, K, psc, psh,
                                      prelu, ps1, ps2, stream);
                 if (rc) return rc;
@@ -329,7 +361,6 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         }
         if (d->d_weight[l]) {
             float* dwp = at<float>(wb, p.dwp[l]);
-            O3D_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)Nl * K, st), "o3d_stack_backward: memset dW");
             const bool tcw = (d->use_tc & 2) && Nl >= 64 && K >= 64 && p.P >= 4096;
             if (tcw) {
                 // tensor-core part: the first floor(K/128)*128 input channels; ragged tail (xyz / box-cloud extras)
