@@ -515,6 +515,77 @@ __global__ void __launch_bounds__(NT, 2)
     }
 }
 
+// wgrad for a handful of input columns — an xyz-only first layer, or the (dx, dy, dz, 0) / box-cloud extras behind the
+// tensor-core part of a first layer:  dW[m, n] += sum_p dY[p, m] * A(X)[p, n],  n < 4*NQ <= 12.
+// No tiles: one streaming pass over dY (the only operand of any size), thread = (4 output channels, every R-th position),
+// U positions of raw loads in flight per thread, block-level reduction through shared-memory REDs.
+template <int NQ, int U>
+__global__ void __launch_bounds__(256, 2)
+    pw_wgrad_skinny_kernel(DyIn din, ActIn ain, int P, int M, int N, int LQ /*threads per position row*/, int chunk,
+                           float* __restrict__ dW, int lddw) {
+    __shared__ float red[256 * 4 * NQ];                  // [256 channels][4*NQ columns]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256 * 4 * NQ; i += 256) red[i] = 0.f;
+    __syncthreads();
+    const int m0 = blockIdx.y * 256;
+    const int cq = tid % LQ, r = tid / LQ, R = 256 / LQ;
+    const int m = m0 + cq * 4;
+    const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
+    float acc[4][4 * NQ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4 * NQ; ++j) acc[i][j] = 0.f;
+    for (int p = pbeg + r; p < pend; p += U * R) {
+        DyRaw d[U];
+        ActRaw x[U][NQ];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            d[u] = fetch_dy(din, p + u * R, pend, m, M);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x[u][q] = fetch_act(ain, p + u * R, pend, q * 4, N);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float4 v = finish_dy(din, d[u], p + u * R, pend, m, M);   // zero outside the slice / channel range
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 xv = finish_act(ain, x[u][q], p + u * R, pend, q * 4, N);
+                const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][q * 4 + j] = fmaf(vv[i], xx[j], acc[i][q * 4 + j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4 * NQ; ++j) atomicAdd(&red[(cq * 4 + i) * 4 * NQ + j], acc[i][j]);
+    __syncthreads();
+    for (int i = tid; i < 256 * 4 * NQ; i += 256) {
+        const int mm = m0 + i / (4 * NQ), n = i % (4 * NQ);
+        if (mm < M && n < N) atomicAdd(dW + (size_t)mm * lddw + n, red[i]);
+    }
+}
+
+template <int NQ, int U>
+int launch_wgrad_skinny(const DyIn& din, const ActIn& ain, int P, int Cout, int Cin, float* dw, int lddw, cudaStream_t st) {
+    const int slabs = (Cout + 255) / 256;
+    const int mq = (std::min(Cout, 256) + 3) / 4;
+    const int LQ = mq <= 16 ? 16 : (mq <= 32 ? 32 : 64);
+    const int R = 256 / LQ;
+    int want = (2 * o3d_num_sms() + slabs - 1) / slabs;
+    int chunk = (P + want - 1) / want;
+    chunk = ((chunk + U * R - 1) / (U * R)) * (U * R);
+    const int nx = (P + chunk - 1) / chunk;
+    pw_wgrad_skinny_kernel<NQ, U><<<dim3(nx, slabs), 256, 0, st>>>(din, ain, P, Cout, Cin, LQ, chunk, dw, lddw);
+    O3D_CHECK_LAUNCH("o3d_pw_wgrad (skinny)");
+    return O3D_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Small per-channel kernels
 __global__ void bn_fwd_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count,
@@ -659,6 +730,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+int o3d_g_no_skinny = 0;
+
 // ============================================================================================================
 extern "C" int o3d_pw_fwd(const float* x, int ldx, const float* in_scale, const float* in_shift, int in_relu,
                           const float* wt, int ldw, const float* bias, int P, int K, int N, float* y, int ldy,
@@ -736,6 +809,11 @@ extern "C" int o3d_pw_wgrad(const float* g, int ldg, const float* y, int ldy, co
     DyIn din = make_dy(g, ldg, y, ldy, a, b, cc, dpool, sel, S, ldp);
     ActIn ain{x, ldx, in_scale, in_shift, in_relu};
     cudaStream_t st = (cudaStream_t)stream;
+    if (Cin <= 12 && P >= 4096 && !o3d_g_no_skinny) {
+        if (Cin <= 4) return launch_wgrad_skinny<1, 4>(din, ain, P, Cout, Cin, dw, lddw, st);
+        if (Cin <= 8) return launch_wgrad_skinny<2, 2>(din, ain, P, Cout, Cin, dw, lddw, st);
+        return launch_wgrad_skinny<3, 2>(din, ain, P, Cout, Cin, dw, lddw, st);
+    }
     const int mt = (Cout + BM - 1) / BM;
     const int bn = Cin <= 64 ? 64 : 128;
     const int ntile = (Cin + bn - 1) / bn;

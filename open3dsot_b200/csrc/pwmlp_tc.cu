@@ -151,6 +151,7 @@ struct TcAct {
 struct TcDy {
     const float* g; int ldg; const float* y; int ldy; const float* a; const float* b; const float* cc;
     const float* dpool; const int32_t* sel; int S; int ldp;
+    int sh;   // S == 1 << sh (pooling group sizes are powers of two on this path)
     struct Coef { float4 a, b, c; bool on; };
     struct Raw { float4 g, y; };
     __device__ __forceinline__ Coef prep(int k, int K) const {
@@ -165,9 +166,10 @@ struct TcDy {
         Raw r;
         const int pp = p < P ? p : P - 1, kk = k < K ? k : 0;
         if (dpool) {   // pooled gradient: [G, ldp] tables, re-used by the S rows of a group (L1 / L2 hits)
-            const int grp = pp / S, s = pp - grp * S;
-            const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + (size_t)grp * ldp + kk));
-            const float4 d = ld4g(dpool + (size_t)grp * ldp + kk);
+            const int grp = pp >> sh, s = pp & (S - 1);
+            const size_t go = (size_t)grp * ldp + kk;
+            const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + go));
+            const float4 d = ld4g(dpool + go);
             r.g = make_float4(sl.x == s ? d.x : 0.f, sl.y == s ? d.y : 0.f, sl.z == s ? d.z : 0.f, sl.w == s ? d.w : 0.f);
         } else {
             r.g = ld4g(g + (size_t)pp * ldg + kk);
@@ -428,37 +430,43 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         const int row0 = pt >> 3;                         // rows row0 + 32*i, i < 4
         int stage = 0, phase = 0;
         if (dbg & 2) P = 0;                               // dbg: nothing is loaded
-        for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
-            const int p0 = tile_of(t) * TC_N;
-            typename BLoad::Raw raw[4];
-            typename BLoad::Coef cf = bl.prep(chunk * 4, K);
-            if (P > 0) {
+        // The (tile, k-block) nest is walked as one flat sequence so that the raw loads of the NEXT item — also when it
+        // is the first k-block of the next position tile — are always in flight while the current one is being stored.
+        int t = blockIdx.x, kb = 0;
+        int p0 = t < n_ptiles ? tile_of(t) * TC_N : 0;
+        typename BLoad::Raw raw[4];
+        typename BLoad::Coef cf = bl.prep(chunk * 4, K);
+        if (P > 0 && t < n_ptiles) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) raw[i] = bl.fetch(p0 + row0 + 32 * i, P, chunk * 4, K);
+            for (int i = 0; i < 4; ++i) raw[i] = bl.fetch(p0 + row0 + 32 * i, P, chunk * 4, K);
+        }
+        while (t < n_ptiles) {
+            o3d_mbar_wait(empty + stage, phase ^ 1);
+            uint8_t* xhi = smem + stage * C::STAGE_BYTES_ + 2 * MT * TILE_BYTES;
+            uint8_t* xlo = xhi + TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = P > 0 ? bl.finish(raw[i], cf, p0 + row0 + 32 * i, P) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t off = sw128(row0 + 32 * i, chunk);
+                *reinterpret_cast<float4*>(xhi + off) = hi_part(v);
+                *reinterpret_cast<float4*>(xlo + off) = lo_part(v);
             }
-            for (int kb = 0; kb < nkb; ++kb) {
-                o3d_mbar_wait(empty + stage, phase ^ 1);
-                uint8_t* xhi = smem + stage * C::STAGE_BYTES_ + 2 * MT * TILE_BYTES;
-                uint8_t* xlo = xhi + TILE_BYTES;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = P > 0 ? bl.finish(raw[i], cf, p0 + row0 + 32 * i, P) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const uint32_t off = sw128(row0 + 32 * i, chunk);
-                    *reinterpret_cast<float4*>(xhi + off) = hi_part(v);
-                    *reinterpret_cast<float4*>(xlo + off) = lo_part(v);
-                }
-                o3d_fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
-                o3d_mbar_arrive(full + stage);
-                if (kb + 1 < nkb) {
-                    const int k = (kb + 1) * TC_K + chunk * 4;
-                    cf = bl.prep(k, K);
-                    if (P > 0) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) raw[i] = bl.fetch(p0 + row0 + 32 * i, P, k, K);
-                    }
-                }
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            o3d_fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
+            o3d_mbar_arrive(full + stage);
+            if (++kb == nkb) {
+                kb = 0;
+                t += gridDim.x;
+                if (t < n_ptiles) p0 = tile_of(t) * TC_N;
             }
+            if (t < n_ptiles) {
+                const int k = kb * TC_K + chunk * 4;
+                cf = bl.prep(k, K);
+                if (P > 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) raw[i] = bl.fetch(p0 + row0 + 32 * i, P, k, K);
+                }
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -534,6 +542,26 @@ __device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int ti
     }
 }
 
+
+// L2 prefetch of one CTA's slice of position rows, paced by the MMA warp's progress (rows consumed, published in shared
+// memory): at most WINDOW rows ahead.  Prefetching the whole slice up front asks for several hundred MB across the grid —
+// more than the 126 MB L2 — and the lines are evicted again before their k-block comes up.
+template <class LA, class LB>
+__device__ __forceinline__ void paced_prefetch(const LA& da, const LB& xb, int pbeg, int pend, volatile int* progress) {
+    constexpr int CH = 128, WINDOW = 3 * CH;
+    int issued = pbeg;
+    while (issued < pend) {
+        const int target = pbeg + *progress + WINDOW;
+        if (issued < target) {
+            da.prefetch_rows(issued, CH, pend);
+            xb.prefetch_rows(issued, CH, pend);
+            issued += CH;
+        } else {
+            __nanosleep(256);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1)
     pw_wgrad_tc_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ dW, int lddw, int dbg) {
     extern __shared__ uint8_t smem_raw[];
@@ -543,6 +571,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     uint64_t* empty = bars + TC_STAGES;
     uint64_t* tfull = bars + 2 * TC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    volatile int* progress = reinterpret_cast<volatile int*>(tmem_slot + 1);   // rows handed to the tensor core so far
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.z * TC_M, n0 = blockIdx.y * TC_N;
@@ -557,6 +586,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
             o3d_mbar_init(empty + s, 1);
         }
         o3d_mbar_init(tfull, 1);
+        *progress = 0;
         o3d_fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 128);
@@ -585,15 +615,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
                 }
                 umma_commit(empty + stage);
                 if (kb == nkb - 1) umma_commit(tfull);
+                *progress = (kb + 1) * TC_K;
             }
             __syncwarp();
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // stream the position rows of this slice into L2, 16 k-blocks (512 rows) at a time
-            for (int p = pbeg; p < pend; p += 512) {
-                da.prefetch_rows(p, 512, pend);
-                xb.prefetch_rows(p, 512, pend);
+        if (lane == 0) {
+            if (dbg & 64) {   // dbg: the old behaviour, whole slice requested up front
+                for (int p = pbeg; p < pend; p += 512) {
+                    da.prefetch_rows(p, 512, pend);
+                    xb.prefetch_rows(p, 512, pend);
+                }
+            } else {
+                paced_prefetch(da, xb, pbeg, pend, progress);
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -667,7 +702,7 @@ __device__ __forceinline__ uint32_t sw_mn2(int p_local, int c4) {   // c4 = floa
 
 template <int MH, int NH>
 __global__ void __launch_bounds__(WG2_THREADS, 1)
-    pw_wgrad_tc2_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ part) {
+    pw_wgrad_tc2_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ part, int dbg) {
     using C = Wg2Cfg<MH, NH>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -676,6 +711,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
     uint64_t* empty = bars + WG2_STAGES;
     uint64_t* tfull = bars + 2 * WG2_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG2_STAGES + 1);
+    volatile int* progress = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.z * 128 * MH, n0 = blockIdx.y * 128 * NH;
@@ -689,6 +725,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
             o3d_mbar_init(empty + s, 1);
         }
         o3d_mbar_init(tfull, 1);
+        *progress = 0;
         o3d_fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, C::TMEM);
@@ -723,15 +760,20 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
                 }
                 umma_commit(empty + stage);
                 if (kb == nkb - 1) umma_commit(tfull);
+                *progress = (kb + 1) * WG2_K;
             }
             __syncwarp();
             if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int p = pbeg; p < pend; p += 512) {
-                da.prefetch_rows(p, 512, pend);
-                xb.prefetch_rows(p, 512, pend);
+            if (dbg & 64) {
+                for (int p = pbeg; p < pend; p += 512) {
+                    da.prefetch_rows(p, 512, pend);
+                    xb.prefetch_rows(p, 512, pend);
+                }
+            } else {
+                paced_prefetch(da, xb, pbeg, pend, progress);
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -865,6 +907,7 @@ __global__ void w_pretile_kernel(const float* __restrict__ W, int ld, int rows, 
 }
 
 int g_tc_debug = 0, g_tc_force_mt = 0;
+inline int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 thread_local int g_tc_rev = 0;   // direction of the next launch (set by the stack sequencer)
 
 template <int MT, class BLoad, class Epi>
@@ -893,7 +936,11 @@ int launch_tc(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cu
 
 }  // namespace
 
-extern "C" void o3d_debug_set(int tc_debug, int force_mt) { g_tc_debug = tc_debug; g_tc_force_mt = force_mt; }
+extern "C" void o3d_debug_set(int tc_debug, int force_mt) {
+    g_tc_debug = tc_debug;
+    g_tc_force_mt = force_mt;
+    o3d_g_no_skinny = (tc_debug & 128) != 0;
+}
 extern "C" void o3d_pw_tc_set_reverse(int rev) { g_tc_rev = rev; }
 
 extern "C" long long o3d_pw_tc_wtile_bytes(int rows, int K) {
@@ -937,7 +984,7 @@ extern "C" int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy,
     O3D_REQUIRE((g || dpool) && wtiles_t && out, O3D_ERR_ARG, "o3d_pw_dgrad_tc: null pointer");
     O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0, O3D_ERR_ARG, "o3d_pw_dgrad_tc: channel counts must be multiples of 4");
     if (P == 0) return O3D_OK;
-    TcDy bl{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp};
+    TcDy bl{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1)};
     TcDgradEpi ep{};
     ep.out = out; ep.ldo = ldo; ep.yprev = yprev; ep.ldyp = ldyp; ep.scale = pscale; ep.shift = pshift; ep.relu = prelu;
     ep.s1g = s1; ep.s2y = s2y;
@@ -953,7 +1000,7 @@ extern "C" int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy,
     O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0 && (ldx & 3) == 0, O3D_ERR_ARG,
                 "o3d_pw_wgrad_tc: channel counts / leading dimensions must be multiples of 4");
     if (P == 0) return O3D_OK;
-    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp};
+    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1)};
     TcAct xb{x, ldx, in_scale, in_shift, in_relu};
     O3D_CUDA(cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "o3d_pw_wgrad_tc");
     const int mt = (Cout + TC_M - 1) / TC_M, nt = (Cin + TC_N - 1) / TC_N;
@@ -984,7 +1031,7 @@ int launch_wgrad2(const TcDy& da, const TcAct& xb, int P, int Cout, int Cin, flo
     int chunk = (P + splits - 1) / splits;
     chunk = ((chunk + WG2_K - 1) / WG2_K) * WG2_K;
     splits = (P + chunk - 1) / chunk;
-    kern<<<dim3(splits, nt, mt), WG2_THREADS, C::SMEM, st>>>(da, xb, P, Cout, Cin, chunk, part);
+    kern<<<dim3(splits, nt, mt), WG2_THREADS, C::SMEM, st>>>(da, xb, P, Cout, Cin, chunk, part, g_tc_debug);
     O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc2");
     dim3 rg((Cin / 4 + 31) / 32, Cout);
     wgrad_reduce_kernel<<<rg, 256, 0, st>>>(part, splits, Mt, Nt, Cout, Cin, dw, lddw);
@@ -1005,7 +1052,7 @@ extern "C" int o3d_pw_wgrad_tc2(const float* g, int ldg, const float* y, int ldy
     O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0 && (ldx & 3) == 0 && (lddw & 3) == 0, O3D_ERR_ARG,
                 "o3d_pw_wgrad_tc2: channel counts / leading dimensions must be multiples of 4");
     if (P == 0) return O3D_OK;
-    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp};
+    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1)};
     TcAct xb{x, ldx, in_scale, in_shift, in_relu};
     cudaStream_t st = (cudaStream_t)stream;
     const bool m2 = Cout > 128, n2 = Cin > 128;

@@ -24,20 +24,26 @@ def main():
     ap.add_argument("--levels", default="0,1,3")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--fwd-only", action="store_true")
-    ap.add_argument("--dbg", type=int, default=0)
+    ap.add_argument("--dbg", default="0", help="comma-separated o3d_debug_set values, one measurement per value")
+    ap.add_argument("--no-dx", action="store_true", help="the stack input needs no gradient (first SA level)")
     ap.add_argument("--force-mt", type=int, default=0)
     a = ap.parse_args()
     chans, P, S = SHAPES[a.shape]
     from open3dsot_b200 import _lib
-    _lib.lib().o3d_debug_set(a.dbg, a.force_mt)
     torch.manual_seed(0)
     mod = pt.SharedMLP(list(chans), bn=True).cuda().train()
     specs = fused.parse_stack(mod)
     x = torch.randn(P, chans[0], device="cuda")
     flops = sum(2 * P * chans[i] * chans[i + 1] for i in range(len(chans) - 1))
-    for lv in [int(v) for v in a.levels.split(",")]:
+    # activation traffic every kernel of the stack has to move at least once (fp32), see DESIGN.md section 4
+    nw = [((c + 3) // 4) * 4 for c in chans]
+    fwd_fl = sum(nw[i] + nw[i + 1] for i in range(len(nw) - 1))
+    bwd_fl = sum(2 * nw[i + 1] + 2 * nw[i] for i in range(len(nw) - 1)) + sum(2 * nw[i + 1] + nw[i] for i in range(len(nw) - 1))
+    gb_f, gb_b = 4e-9 * P * fwd_fl, 4e-9 * P * bwd_fl
+    for lv, dbg in [(int(v), int(d)) for v in a.levels.split(",") for d in a.dbg.split(",")]:
+        _lib.lib().o3d_debug_set(dbg, a.force_mt)
         runtime.set_tc(lv)
-        xin = x.clone().requires_grad_(not a.fwd_only)
+        xin = x.clone().requires_grad_(not a.fwd_only and not a.no_dx)
         for _ in range(2):
             out = fused.mlp_stack(xin, specs, S, True)
             if not a.fwd_only:
@@ -58,8 +64,8 @@ def main():
             tb += e[1].elapsed_time(e[2])
         tf /= a.iters
         tb /= a.iters
-        print(f"shape {a.shape} P={P} level {lv}: fwd {tf:.3f} ms ({flops / tf / 1e9:.1f} TFLOP/s)  bwd {tb:.3f} ms"
-              f" ({2 * flops / max(tb, 1e-9) / 1e9:.1f} TFLOP/s)")
+        print(f"shape {a.shape} P={P} level {lv} dbg {dbg}: fwd {tf:.3f} ms ({flops / tf / 1e9:.1f} TFLOP/s, {gb_f / tf * 1e3:.0f} GB/s)"
+              f"  bwd {tb:.3f} ms ({2 * flops / max(tb, 1e-9) / 1e9:.1f} TFLOP/s, {gb_b / max(tb, 1e-9) * 1e3:.0f} GB/s)", flush=True)
 
 
 if __name__ == "__main__":
