@@ -109,6 +109,12 @@ __device__ __forceinline__ void prefetch_dy(const DyIn& in, int p0, int rows, in
     const size_t n = (size_t)min(rows, P - p0);
     if (!in.dpool) o3d_prefetch_l2(in.g + (size_t)p0 * in.ldg, n * in.ldg * sizeof(float));
     if (in.a) o3d_prefetch_l2(in.y + (size_t)p0 * in.ldy, n * in.ldy * sizeof(float));
+    if (in.dpool) {   // pooled-gradient tables of the groups these rows belong to
+        const int g0 = p0 / in.S, g1 = (p0 + (int)n - 1) / in.S;
+        const size_t bytes = (size_t)(g1 - g0 + 1) * in.ldp * sizeof(float);
+        o3d_prefetch_l2(in.dpool + (size_t)g0 * in.ldp, bytes);
+        o3d_prefetch_l2(in.sel + (size_t)g0 * in.ldp, bytes);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -120,7 +120,8 @@ __device__ __forceinline__ float4 ld4g(const float* p) { return __ldg(reinterpre
 struct TcAct {
     const float* x; int ld; const float* scale; const float* shift; int relu;
     struct Coef { float4 s, t; bool on; };
-    struct Raw { float4 v; };
+    // raw operand rows of one thread for one k-block: rows p0 + i * stride, i < R
+    template <int R> struct Batch { float4 v[R]; };
     __device__ __forceinline__ Coef prep(int k, int K) const {
         Coef c;
         c.on = k < K;
@@ -129,15 +130,20 @@ struct TcAct {
         if (c.on && scale) { c.s = ld4g(scale + k); c.t = ld4g(shift + k); }
         return c;
     }
-    // unconditional, always-in-range load (clamped indices): nothing here depends on loaded data, so a batch of
-    // fetches is issued back to back and all of them are in flight together; masking happens in finish()
-    __device__ __forceinline__ Raw fetch(int p, int P, int k, int K) const {
-        Raw r;
-        r.v = ld4g(x + (size_t)(p < P ? p : P - 1) * ld + (k < K ? k : 0));
-        return r;
+    // unconditional, always-in-range loads (clamped indices): nothing here depends on loaded data, so the whole batch is
+    // issued back to back and is in flight together; masking and the transform happen in finish()
+    template <int R>
+    __device__ __forceinline__ void fetch(Batch<R>& b, int p0, int stride, int P, int k, int K) const {
+        const int kk = k < K ? k : 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int p = p0 + i * stride;
+            b.v[i] = ld4g(x + (size_t)(p < P ? p : P - 1) * ld + kk);
+        }
     }
-    __device__ __forceinline__ float4 finish(const Raw& r, const Coef& c, int p, int P) const {
-        float4 v = r.v;
+    template <int R>
+    __device__ __forceinline__ float4 finish(const Batch<R>& b, const Coef& c, int i, int p, int P) const {
+        float4 v = b.v[i];
         if (!(c.on && p < P)) return make_float4(0.f, 0.f, 0.f, 0.f);
         if (scale) { v.x = fmaf(v.x, c.s.x, c.t.x); v.y = fmaf(v.y, c.s.y, c.t.y); v.z = fmaf(v.z, c.s.z, c.t.z); v.w = fmaf(v.w, c.s.w, c.t.w); }
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -152,8 +158,13 @@ struct TcDy {
     const float* g; int ldg; const float* y; int ldy; const float* a; const float* b; const float* cc;
     const float* dpool; const int32_t* sel; int S; int ldp;
     int sh;   // S == 1 << sh (pooling group sizes are powers of two on this path)
+    int dbg;  // profiling experiments: 256 = no sel / dpool loads, 512 = no y load
     struct Coef { float4 a, b, c; bool on; };
-    struct Raw { float4 g, y; };
+    // raw operand rows of one thread for one k-block: rows p0 + i * stride, i < R (R >= 2).
+    // Pooled gradient: when all R rows fall into one pooling group — the usual case, a thread's rows are neighbours — the
+    // two [G, ldp] tables are read ONCE (g[0] = dpool entry, g[1] = bit pattern of sel) and the per-row select moves to
+    // finish(); selecting inside fetch() would make every row wait for its own table load before the next row's loads go out.
+    template <int R> struct Batch { float4 g[R]; float4 y[R]; bool shared; };
     __device__ __forceinline__ Coef prep(int k, int K) const {
         Coef c;
         c.on = k < K;
@@ -162,27 +173,63 @@ struct TcDy {
         if (c.on && a) { c.a = ld4g(a + k); c.b = ld4g(b + k); c.c = ld4g(cc + k); }
         return c;
     }
-    __device__ __forceinline__ Raw fetch(int p, int P, int k, int K) const {
-        Raw r;
-        const int pp = p < P ? p : P - 1, kk = k < K ? k : 0;
-        if (dpool) {   // pooled gradient: [G, ldp] tables, re-used by the S rows of a group (L1 / L2 hits)
-            const int grp = pp >> sh, s = pp & (S - 1);
-            const size_t go = (size_t)grp * ldp + kk;
-            const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + go));
-            const float4 d = ld4g(dpool + go);
-            r.g = make_float4(sl.x == s ? d.x : 0.f, sl.y == s ? d.y : 0.f, sl.z == s ? d.z : 0.f, sl.w == s ? d.w : 0.f);
+    template <int R>
+    __device__ __forceinline__ void fetch(Batch<R>& bt, int p0, int stride, int P, int k, int K) const {
+        static_assert(R >= 2, "a batch holds the two pooled-gradient tables in g[0], g[1]");
+        const int kk = k < K ? k : 0;
+        bt.shared = false;
+        if (dpool) {
+            const int pf = p0 < P ? p0 : P - 1;
+            const int pe = p0 + (R - 1) * stride;
+            const int pl = pe < P ? pe : P - 1;
+            if ((pf >> sh) == (pl >> sh)) {
+                bt.shared = true;
+                const size_t go = (size_t)(pf >> sh) * ldp + kk;
+                if (!(dbg & 256)) {
+                    bt.g[0] = ld4g(dpool + go);
+                    const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + go));
+                    bt.g[1] = make_float4(__int_as_float(sl.x), __int_as_float(sl.y), __int_as_float(sl.z), __int_as_float(sl.w));
+                } else {
+                    bt.g[0] = bt.g[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const int p = p0 + i * stride, pp = p < P ? p : P - 1;
+                    const int s = pp & (S - 1);
+                    const size_t go = (size_t)(pp >> sh) * ldp + kk;
+                    const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + go));
+                    const float4 d = ld4g(dpool + go);
+                    bt.g[i] = make_float4(sl.x == s ? d.x : 0.f, sl.y == s ? d.y : 0.f, sl.z == s ? d.z : 0.f, sl.w == s ? d.w : 0.f);
+                }
+            }
         } else {
-            r.g = ld4g(g + (size_t)pp * ldg + kk);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int p = p0 + i * stride;
+                bt.g[i] = ld4g(g + (size_t)(p < P ? p : P - 1) * ldg + kk);
+            }
         }
-        r.y = a ? ld4g(y + (size_t)pp * ldy + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
-        return r;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int p = p0 + i * stride;
+            bt.y[i] = (a && !(dbg & 512)) ? ld4g(y + (size_t)(p < P ? p : P - 1) * ldy + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
-    __device__ __forceinline__ float4 finish(const Raw& r, const Coef& c, int p, int P) const {
+    template <int R>
+    __device__ __forceinline__ float4 finish(const Batch<R>& bt, const Coef& c, int i, int p, int P) const {
         if (!(c.on && p < P)) return make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 v = r.g;
+        float4 v = bt.g[i];
+        if (bt.shared) {
+            const int s = p & (S - 1);
+            const float4 d = bt.g[0], sl = bt.g[1];
+            v = make_float4(__float_as_int(sl.x) == s ? d.x : 0.f, __float_as_int(sl.y) == s ? d.y : 0.f,
+                            __float_as_int(sl.z) == s ? d.z : 0.f, __float_as_int(sl.w) == s ? d.w : 0.f);
+        }
         if (a) {
-            v.x = fmaf(c.a.x, v.x, fmaf(c.c.x, r.y.x, c.b.x)); v.y = fmaf(c.a.y, v.y, fmaf(c.c.y, r.y.y, c.b.y));
-            v.z = fmaf(c.a.z, v.z, fmaf(c.c.z, r.y.z, c.b.z)); v.w = fmaf(c.a.w, v.w, fmaf(c.c.w, r.y.w, c.b.w));
+            const float4 yy = bt.y[i];
+            v.x = fmaf(c.a.x, v.x, fmaf(c.c.x, yy.x, c.b.x)); v.y = fmaf(c.a.y, v.y, fmaf(c.c.y, yy.y, c.b.y));
+            v.z = fmaf(c.a.z, v.z, fmaf(c.c.z, yy.z, c.b.z)); v.w = fmaf(c.a.w, v.w, fmaf(c.c.w, yy.w, c.b.w));
         }
         return v;
     }
@@ -191,10 +238,19 @@ struct TcDy {
         const size_t n = (size_t)min(rows, P - p0);
         if (!dpool) o3d_prefetch_l2(g + (size_t)p0 * ldg, n * ldg * sizeof(float));
         if (a) o3d_prefetch_l2(y + (size_t)p0 * ldy, n * ldy * sizeof(float));
+        if (dpool) {   // the [G, ldp] tables of the groups these rows belong to: without this every k-block of a tile starts
+                       // with a cold miss on a new 128-byte line of each table
+            const int g0 = p0 >> sh, g1 = (p0 + (int)n - 1) >> sh;
+            const size_t bytes = (size_t)(g1 - g0 + 1) * ldp * sizeof(float);
+            o3d_prefetch_l2(dpool + (size_t)g0 * ldp, bytes);
+            o3d_prefetch_l2(sel + (size_t)g0 * ldp, bytes);
+        }
     }
 };
 
 // ---- epilogues: thread = one output channel `ch`, called once per 32-position column group ------------------
+// LD: compile-time row stride of y (0 = use the runtime ldy)
+template <int LD>
 struct TcFwdEpi {
     float* y; int ldy; const float* bias; double* sum; double* sumsq;
     int S, log2S; float* ymax; float* ymin; int32_t* arg; int ldp;
@@ -206,26 +262,64 @@ struct TcFwdEpi {
         mx = -INFINITY; mn = INFINITY; ax = an = 0;
     }
     __device__ __forceinline__ void prefetch(int, int, int, int) {}
+    // Fast path = a full group of 16 positions that lies inside one pooling group (S >= 16, the set-abstraction case):
+    // no per-element range or group-boundary test, the max / min / first-arg scan is local to the 16 values and is merged
+    // into the running (mx, ax, mn, an) of the pooling group with two compares.  Everything else takes the element-wise path.
     __device__ __forceinline__ void group(const uint32_t (&r)[16], int ch, int Nw, int pbase, int P) {
         if (ch >= Nw) return;
         float s1 = 0.f, s2 = 0.f;
         const int smask = S - 1;
         float* yp = y ? y + (size_t)pbase * ldy + ch : nullptr;
+        if (pbase + 16 <= P && (S == 0 || S >= 16)) {
+            float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (pbase + j >= P) break;
-            const float v = __uint_as_float(r[j]) + bv;
-            if (yp) yp[(size_t)j * ldy] = v;
-            s1 += v;
-            s2 = fmaf(v, v, s2);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bv;
+            if (yp) {
+                const size_t st = LD ? (size_t)LD : (size_t)ldy;   // compile-time stride -> immediate store offsets
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yp[j * st] = v[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                s1 += v[j];
+                s2 = fmaf(v[j], v[j], s2);
+            }
             if (S > 0) {
-                const int s = (pbase + j) & smask;
-                if (s == 0) { mx = -INFINITY; mn = INFINITY; ax = an = 0; }
-                if (v > mx) { mx = v; ax = s; }
-                if (v < mn) { mn = v; an = s; }
-                if (s == smask) {
-                    const size_t o = (size_t)((pbase + j) >> log2S) * ldp + ch;
+                float gm = v[0], gn = v[0];
+                int ga = 0, gb = 0;
+#pragma unroll
+                for (int j = 1; j < 16; ++j) {
+                    if (v[j] > gm) { gm = v[j]; ga = j; }
+                    if (v[j] < gn) { gn = v[j]; gb = j; }
+                }
+                const int s0 = pbase & smask;
+                if (s0 == 0) { mx = gm; ax = ga; mn = gn; an = gb; }
+                else {
+                    if (gm > mx) { mx = gm; ax = s0 + ga; }
+                    if (gn < mn) { mn = gn; an = s0 + gb; }
+                }
+                if (s0 + 16 == S) {
+                    const size_t o = (size_t)(pbase >> log2S) * ldp + ch;
                     ymax[o] = mx; ymin[o] = mn; arg[o] = ax | (an << 16);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (pbase + j >= P) break;
+                const float v = __uint_as_float(r[j]) + bv;
+                if (yp) yp[(size_t)j * ldy] = v;
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+                if (S > 0) {
+                    const int s = (pbase + j) & smask;
+                    if (s == 0) { mx = -INFINITY; mn = INFINITY; ax = an = 0; }
+                    if (v > mx) { mx = v; ax = s; }
+                    if (v < mn) { mn = v; an = s; }
+                    if (s == smask) {
+                        const size_t o = (size_t)((pbase + j) >> log2S) * ldp + ch;
+                        ymax[o] = mx; ymin[o] = mn; arg[o] = ax | (an << 16);
+                    }
                 }
             }
         }
@@ -240,6 +334,8 @@ struct TcFwdEpi {
     }
 };
 
+// LD: compile-time row stride shared by out and yprev (0 = use the runtime ldo / ldyp)
+template <int LD>
 struct TcDgradEpi {
     float* out; int ldo; const float* yprev; int ldyp; const float* scale; const float* shift; int relu;
     double* s1g; double* s2y;
@@ -254,22 +350,53 @@ struct TcDgradEpi {
     __device__ __forceinline__ void prefetch(int ch, int Nw, int pbase, int P) {
         if (!yprev || ch >= Nw) return;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) yv[j] = (pbase + j < P) ? __ldg(yprev + (size_t)(pbase + j) * ldyp + ch) : 0.f;
+        if (pbase + 16 <= P) {
+            const float* yp = yprev + (size_t)pbase * ldyp + ch;
+            const size_t st = LD ? (size_t)LD : (size_t)ldyp;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) yv[j] = __ldg(yp + j * st);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int pj = min(pbase + j, P - 1);      // clamped: the load is unconditional, group() masks by range
+                yv[j] = __ldg(yprev + (size_t)pj * ldyp + ch);
+            }
+        }
     }
     __device__ __forceinline__ void group(const uint32_t (&r)[16], int ch, int Nw, int pbase, int P) {
         if (ch >= Nw) return;
         float s1 = 0.f, s2 = 0.f;
         float* op = out + (size_t)pbase * ldo + ch;
+        if (pbase + 16 <= P) {          // full group: no per-element range test
+            float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (pbase + j >= P) break;
-            float v = __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
             if (yprev) {
-                if (relu && !(fmaf(yv[j], sc, sh) > 0.f)) v = 0.f;
-                s2 = fmaf(v, yv[j], s2);
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaf(yv[j], sc, sh) > 0.f ? v[j] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s2 = fmaf(v[j], yv[j], s2);
             }
-            s1 += v;
-            op[(size_t)j * ldo] = v;
+            const size_t st = LD ? (size_t)LD : (size_t)ldo;       // compile-time stride -> immediate store offsets
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                s1 += v[j];
+                op[j * st] = v[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (pbase + j >= P) break;
+                float v = __uint_as_float(r[j]);
+                if (yprev) {
+                    if (relu && !(fmaf(yv[j], sc, sh) > 0.f)) v = 0.f;
+                    s2 = fmaf(v, yv[j], s2);
+                }
+                s1 += v;
+                op[(size_t)j * ldo] = v;
+            }
         }
         d1 += (double)s1;
         d2 += (double)s2;
@@ -427,27 +554,24 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         const int pw = warp < 4 ? warp - 2 : warp - 10;   // producer warp 0..7
         const int pt = pw * 32 + lane;                    // 0..255
         const int chunk = pt & 7;                         // 16-byte chunk (4 channels) inside the 128-byte row
-        const int row0 = pt >> 3;                         // rows row0 + 32*i, i < 4
+        const int row0 = (pt >> 3) * 4;                   // 4 neighbouring rows row0 + i, i < 4 (one pooling group)
         int stage = 0, phase = 0;
         if (dbg & 2) P = 0;                               // dbg: nothing is loaded
         // The (tile, k-block) nest is walked as one flat sequence so that the raw loads of the NEXT item — also when it
         // is the first k-block of the next position tile — are always in flight while the current one is being stored.
         int t = blockIdx.x, kb = 0;
         int p0 = t < n_ptiles ? tile_of(t) * TC_N : 0;
-        typename BLoad::Raw raw[4];
+        typename BLoad::template Batch<4> raw;
         typename BLoad::Coef cf = bl.prep(chunk * 4, K);
-        if (P > 0 && t < n_ptiles) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) raw[i] = bl.fetch(p0 + row0 + 32 * i, P, chunk * 4, K);
-        }
+        if (P > 0 && t < n_ptiles) bl.fetch(raw, p0 + row0, 1, P, chunk * 4, K);
         while (t < n_ptiles) {
             o3d_mbar_wait(empty + stage, phase ^ 1);
             uint8_t* xhi = smem + stage * C::STAGE_BYTES_ + 2 * MT * TILE_BYTES;
             uint8_t* xlo = xhi + TILE_BYTES;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 v = P > 0 ? bl.finish(raw[i], cf, p0 + row0 + 32 * i, P) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const uint32_t off = sw128(row0 + 32 * i, chunk);
+                const float4 v = P > 0 ? bl.finish(raw, cf, i, p0 + row0 + i, P) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t off = sw128(row0 + i, chunk);
                 *reinterpret_cast<float4*>(xhi + off) = hi_part(v);
                 *reinterpret_cast<float4*>(xlo + off) = lo_part(v);
             }
@@ -461,10 +585,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
             if (t < n_ptiles) {
                 const int k = kb * TC_K + chunk * 4;
                 cf = bl.prep(k, K);
-                if (P > 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) raw[i] = bl.fetch(p0 + row0 + 32 * i, P, k, K);
-                }
+                if (P > 0) bl.fetch(raw, p0 + row0, 1, P, k, K);
             }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -511,33 +632,27 @@ __device__ __forceinline__ uint32_t sw128_mn(int p_local, int c4) {   // c4 = fl
 // handed to the tensor core; transform + hi/lo split happen at store time.
 template <class L, class KPos>
 __device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int tile_off, uint64_t* full, uint64_t* empty,
-                                              int pt, int c_base, int CH, KPos kpos, int pend, int nkb) {
+                                              int pt, int c_base, int CH, KPos kpos, int pend, int nkb, int dbg) {
     const int c4 = pt & 31, prow0 = pt >> 5;      // rows prow0 + 4*i
     const int ch0 = c_base + c4 * 4;
     const typename L::Coef cf = ld.prep(ch0, CH);
-    typename L::Raw raw[8];
+    typename L::template Batch<8> raw = {};
     int stage = 0, phase = 0;
-    if (nkb > 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) raw[i] = ld.fetch(kpos(0) + prow0 + 4 * i, pend, ch0, CH);
-    }
+    if (nkb > 0 && !(dbg & 2)) ld.fetch(raw, kpos(0) + prow0, 4, pend, ch0, CH);
     for (int kb = 0; kb < nkb; ++kb) {
         o3d_mbar_wait(empty + stage, phase ^ 1);
         uint8_t* hi = smem + stage * STAGE_BYTES + tile_off;
         uint8_t* lo = hi + TILE_BYTES;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 v = ld.finish(raw[i], cf, kpos(kb) + prow0 + 4 * i, pend);
+            const float4 v = ld.finish(raw, cf, i, kpos(kb) + prow0 + 4 * i, pend);
             const uint32_t off = sw128_mn(prow0 + 4 * i, c4);
             *reinterpret_cast<float4*>(hi + off) = hi_part(v);
             *reinterpret_cast<float4*>(lo + off) = lo_part(v);
         }
         o3d_fence_proxy_async();
         o3d_mbar_arrive(full + stage);
-        if (kb + 1 < nkb) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) raw[i] = ld.fetch(kpos(kb + 1) + prow0 + 4 * i, pend, ch0, CH);
-        }
+        if (kb + 1 < nkb && !(dbg & 2)) ld.fetch(raw, kpos(kb + 1) + prow0, 4, pend, ch0, CH);
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
     }
 }
@@ -654,8 +769,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     } else if (warp >= 8) {
         // producers: warps 8-11 -> A (dY, channels m0..), warps 12-15 -> B (X, channels n0..)
         const int pt = (threadIdx.x - 256) & 127;
-        if (warp < 12) wgrad_produce(da, smem, 0, full, empty, pt, m0, M, kpos, pend, nkb);
-        else wgrad_produce(xb, smem, 2 * TILE_BYTES, full, empty, pt, n0, N, kpos, pend, nkb);
+        if (warp < 12) wgrad_produce(da, smem, 0, full, empty, pt, m0, M, kpos, pend, nkb, dbg);
+        else wgrad_produce(xb, smem, 2 * TILE_BYTES, full, empty, pt, n0, N, kpos, pend, nkb, dbg);
     }
     tc_fence_before();
     __syncthreads();
@@ -815,13 +930,12 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
         const int cb4 = pt % CB, pb0 = pt / CB, sbs = 256 / CB;
         const TcDy::Coef cfa = da.prep(m0 + ca4 * 4, M);
         const TcAct::Coef cfb = xb.prep(n0 + cb4 * 4, N);
-        TcDy::Raw ra[RA];
-        TcAct::Raw rb[RB];
+        TcDy::Batch<RA> ra = {};
+        TcAct::Batch<RB> rb = {};
         auto fetch = [&](int kb) {
-#pragma unroll
-            for (int i = 0; i < RA; ++i) ra[i] = da.fetch(kpos(kb) + pa0 + sa * i, pend, m0 + ca4 * 4, M);
-#pragma unroll
-            for (int i = 0; i < RB; ++i) rb[i] = xb.fetch(kpos(kb) + pb0 + sbs * i, pend, n0 + cb4 * 4, N);
+            if (dbg & 2) return;
+            da.fetch(ra, kpos(kb) + pa0, sa, pend, m0 + ca4 * 4, M);
+            xb.fetch(rb, kpos(kb) + pb0, sbs, pend, n0 + cb4 * 4, N);
         };
         int stage = 0, phase = 0;
         if (nkb > 0) fetch(0);
@@ -834,7 +948,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < RA; ++i) {
                 const int pl = pa0 + sa * i;
-                const float4 v = da.finish(ra[i], cfa, kpos(kb) + pl, pend);
+                const float4 v = da.finish(ra, cfa, i, kpos(kb) + pl, pend);
                 const uint32_t off = sw_mn2<MH>(pl, ca4);
                 *reinterpret_cast<float4*>(a_hi + off) = hi_part(v);
                 *reinterpret_cast<float4*>(a_lo + off) = lo_part(v);
@@ -842,7 +956,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
                 const int pl = pb0 + sbs * i;
-                const float4 v = xb.finish(rb[i], cfb, kpos(kb) + pl, pend);
+                const float4 v = xb.finish(rb, cfb, i, kpos(kb) + pl, pend);
                 const uint32_t off = sw_mn2<NH>(pl, cb4);
                 *reinterpret_cast<float4*>(b_hi + off) = hi_part(v);
                 *reinterpret_cast<float4*>(b_lo + off) = lo_part(v);
@@ -927,11 +1041,40 @@ int launch_tc_mt(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi,
 }
 
 // Nw must be a multiple of 128 when more than one channel tile exists with MT = 2 (weight tiles are read pairwise).
-template <class BLoad, class Epi>
+inline bool tc_two_tiles(int Nw) { return ((Nw + TC_M - 1) / TC_M) % 2 == 0 && g_tc_force_mt != 1; }
+
+// MTMASK: which MT variants this (loader, epilogue) pair is instantiated for (bit 0: MT = 1, bit 1: MT = 2)
+template <int MTMASK, class BLoad, class Epi>
 int launch_tc(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cudaStream_t st, const char* name) {
-    const int mt = (Nw + TC_M - 1) / TC_M;
-    if (mt % 2 == 0 && g_tc_force_mt != 1) return launch_tc_mt<2>(bl, wtiles, P, K, Nw, epi, st, name);
-    return launch_tc_mt<1>(bl, wtiles, P, K, Nw, epi, st, name);
+    if constexpr ((MTMASK & 2) != 0) {
+        if (tc_two_tiles(Nw)) return launch_tc_mt<2>(bl, wtiles, P, K, Nw, epi, st, name);
+    }
+    if constexpr ((MTMASK & 1) != 0) {
+        if (!tc_two_tiles(Nw)) return launch_tc_mt<1>(bl, wtiles, P, K, Nw, epi, st, name);
+    }
+    o3d_set_error("%s: no kernel variant for %d output channels", name, Nw);
+    return O3D_ERR_ARG;
+}
+
+template <int LD, int MTMASK>
+int launch_fwd(const TcAct& bl, const void* wtiles, const float* bias, int P, int K, int Nw, float* y, int ldy, double* sum,
+               double* sumsq, int S, float* ymax, float* ymin, int32_t* arg, int ldp, cudaStream_t st) {
+    TcFwdEpi<LD> ep{};
+    ep.y = y; ep.ldy = ldy; ep.bias = bias; ep.sum = sum; ep.sumsq = sumsq;
+    ep.S = S; ep.ymax = ymax; ep.ymin = ymin; ep.arg = arg; ep.ldp = ldp;
+    ep.log2S = 0;
+    while ((1 << ep.log2S) < S) ++ep.log2S;
+    return launch_tc<MTMASK>(bl, (const uint8_t*)wtiles, P, K, Nw, ep, st, "o3d_pw_fwd_tc");
+}
+
+template <int LD, int MTMASK>
+int launch_dgrad(const TcDy& bl, const void* wtiles_t, int P, int Cout, int Cin, float* out, int ldo, const float* yprev,
+                 int ldyp, const float* pscale, const float* pshift, int prelu, double* s1, double* s2y, cudaStream_t st) {
+    TcDgradEpi<LD> ep{};
+    ep.out = out; ep.ldo = ldo; ep.yprev = yprev; ep.ldyp = ldyp; ep.scale = pscale; ep.shift = pshift; ep.relu = prelu;
+    ep.s1g = s1; ep.s2y = s2y;
+    // GEMM: D[cin, pos] = sum_cout Wt[cin, cout] * dY[pos, cout]  ->  "K" = Cout, "Nw" = Cin
+    return launch_tc<MTMASK>(bl, (const uint8_t*)wtiles_t, P, Cout, Cin, ep, st, "o3d_pw_dgrad_tc");
 }
 
 }  // namespace
@@ -968,12 +1111,15 @@ extern "C" int o3d_pw_fwd_tc(const float* x, int ldx, const float* in_scale, con
     if (P == 0) return O3D_OK;
     const int Nw = (N + 3) & ~3;
     TcAct bl{x, ldx, in_scale, in_shift, in_relu};
-    TcFwdEpi ep{};
-    ep.y = y; ep.ldy = ldy; ep.bias = bias; ep.sum = sum; ep.sumsq = sumsq;
-    ep.S = S; ep.ymax = ymax; ep.ymin = ymin; ep.arg = arg; ep.ldp = ldp;
-    ep.log2S = 0;
-    while ((1 << ep.log2S) < S) ++ep.log2S;
-    return launch_tc(bl, (const uint8_t*)wtiles, P, K, Nw, ep, (cudaStream_t)stream, "o3d_pw_fwd_tc");
+    // the usual activation widths get a compile-time row stride (immediate store offsets in the epilogue)
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool two = tc_two_tiles(Nw);
+#define O3D_FWD_ARGS bl, wtiles, bias, P, K, Nw, y, ldy, sum, sumsq, S, ymax, ymin, arg, ldp, st
+    if (ldy == 64 && !two) return launch_fwd<64, 1>(O3D_FWD_ARGS);
+    if (ldy == 128 && !two) return launch_fwd<128, 1>(O3D_FWD_ARGS);
+    if (ldy == 256 && two) return launch_fwd<256, 2>(O3D_FWD_ARGS);
+    return launch_fwd<0, 3>(O3D_FWD_ARGS);
+#undef O3D_FWD_ARGS
 }
 
 extern "C" int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
@@ -984,12 +1130,16 @@ extern "C" int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy,
     O3D_REQUIRE((g || dpool) && wtiles_t && out, O3D_ERR_ARG, "o3d_pw_dgrad_tc: null pointer");
     O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0, O3D_ERR_ARG, "o3d_pw_dgrad_tc: channel counts must be multiples of 4");
     if (P == 0) return O3D_OK;
-    TcDy bl{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1)};
-    TcDgradEpi ep{};
-    ep.out = out; ep.ldo = ldo; ep.yprev = yprev; ep.ldyp = ldyp; ep.scale = pscale; ep.shift = pshift; ep.relu = prelu;
-    ep.s1g = s1; ep.s2y = s2y;
-    // GEMM: D[cin, pos] = sum_cout Wt[cin, cout] * dY[pos, cout]  ->  "K" = Cout, "Nw" = Cin
-    return launch_tc(bl, (const uint8_t*)wtiles_t, P, Cout, Cin, ep, (cudaStream_t)stream, "o3d_pw_dgrad_tc");
+    TcDy bl{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1), g_tc_debug};
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool two = tc_two_tiles(Cin);
+    const int ld = (!yprev || ldyp == ldo) ? ldo : 0;   // one compile-time stride serves both out and yprev
+#define O3D_DG_ARGS bl, wtiles_t, P, Cout, Cin, out, ldo, yprev, ldyp, pscale, pshift, prelu, s1, s2y, st
+    if (ld == 64 && !two) return launch_dgrad<64, 1>(O3D_DG_ARGS);
+    if (ld == 128 && !two) return launch_dgrad<128, 1>(O3D_DG_ARGS);
+    if (ld == 256 && two) return launch_dgrad<256, 2>(O3D_DG_ARGS);
+    return launch_dgrad<0, 3>(O3D_DG_ARGS);
+#undef O3D_DG_ARGS
 }
 
 extern "C" int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
@@ -1000,7 +1150,7 @@ extern "C" int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy,
     O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0 && (ldx & 3) == 0, O3D_ERR_ARG,
                 "o3d_pw_wgrad_tc: channel counts / leading dimensions must be multiples of 4");
     if (P == 0) return O3D_OK;
-    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1)};
+    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1), g_tc_debug};
     TcAct xb{x, ldx, in_scale, in_shift, in_relu};
     O3D_CUDA(cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "o3d_pw_wgrad_tc");
     const int mt = (Cout + TC_M - 1) / TC_M, nt = (Cin + TC_N - 1) / TC_N;
@@ -1052,7 +1202,7 @@ extern "C" int o3d_pw_wgrad_tc2(const float* g, int ldg, const float* y, int ldy
     O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0 && (ldx & 3) == 0 && (lddw & 3) == 0, O3D_ERR_ARG,
                 "o3d_pw_wgrad_tc2: channel counts / leading dimensions must be multiples of 4");
     if (P == 0) return O3D_OK;
-    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1)};
+    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1), g_tc_debug};
     TcAct xb{x, ldx, in_scale, in_shift, in_relu};
     cudaStream_t st = (cudaStream_t)stream;
     const bool m2 = Cout > 128, n2 = Cin > 128;

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--fwd-only", action="store_true")
     ap.add_argument("--dbg", default="0", help="comma-separated o3d_debug_set values, one measurement per value")
+    ap.add_argument("--profile", action="store_true", help="print per-kernel device times of one fwd+bwd (CUPTI)")
     ap.add_argument("--no-dx", action="store_true", help="the stack input needs no gradient (first SA level)")
     ap.add_argument("--force-mt", type=int, default=0)
     a = ap.parse_args()
@@ -64,6 +65,19 @@ def main():
             tb += e[1].elapsed_time(e[2])
         tf /= a.iters
         tb /= a.iters
+        if a.profile:
+            from torch.profiler import profile, ProfilerActivity
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(3):
+                    out = fused.mlp_stack(xin, specs, S, True)
+                    if not a.fwd_only:
+                        out.backward(torch.ones_like(out))
+                torch.cuda.synchronize()
+            evs = [e for e in prof.events() if e.device_type.name == "CUDA"]
+            n = len(evs) // 3
+            for e in evs[2 * n:]:
+                if e.device_time > 8:
+                    print(f"    {e.device_time:9.1f} us  {e.name[:110]}")
         print(f"shape {a.shape} P={P} level {lv} dbg {dbg}: fwd {tf:.3f} ms ({flops / tf / 1e9:.1f} TFLOP/s, {gb_f / tf * 1e3:.0f} GB/s)"
               f"  bwd {tb:.3f} ms ({2 * flops / max(tb, 1e-9) / 1e9:.1f} TFLOP/s, {gb_b / max(tb, 1e-9) * 1e3:.0f} GB/s)", flush=True)
 
