@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--fused", type=int, default=None, help="override O3D_FUSED (1 = fused kernels, 0 = composed)")
     ap.add_argument("--tc", type=int, default=None, help="override O3D_TC (0 = CUDA cores, 1 = tcgen05 fwd+dgrad, 3 = + wgrad)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
+    ap.add_argument("--kernel-table", default=None, metavar="FILE",
+                    help="also write the per-kernel device times of 3 steps (CUPTI, no replay, warm caches) to FILE")
     ap.add_argument("--cfg", default=None, help="other config to exercise (P2B_Car.yaml, M2_track_kitti.yaml, ...): a parity / "
                     "plumbing run of BASELINE.json configs[2..4], NOT the headline metric")
     return ap.parse_args()
@@ -237,6 +239,30 @@ def roofline_probe(dev, batch_pairs):
             "frac_of_tensor_roof": tf / tensor_peak, "frac_of_hbm_roof": gbs / peaks["hbm_gbs"]}
 
 
+def kernel_table(eng, batches, path, steps=3):
+    """Per-kernel device time of `steps` training steps as CUPTI records them (activity tracing: no replay, no
+    serialisation beyond the step's own stream order).  Not a bench value: tracing adds a little launch overhead."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(steps):
+            eng.step(batches[i % len(batches)])
+        torch.cuda.synchronize()
+    agg = {}
+    for e in prof.events():
+        if e.device_type.name != "CUDA":
+            continue
+        a = agg.setdefault(e.name, [0, 0.0])
+        a[0] += 1
+        a[1] += e.device_time
+    total = sum(v[1] for v in agg.values())
+    with open(path, "w") as f:
+        f.write(f"# CUPTI kernel activity, {steps} steps; total kernel time {total / steps / 1e3:.3f} ms per step\n")
+        f.write("#  share   ms/step  launches/step  kernel\n")
+        for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{100 * us / total:7.2f}% {us / steps / 1e3:9.3f} {n / steps:8.1f}  {name[:150]}\n")
+
+
 def run_ours(args):
     from open3dsot_b200 import ddp, ops, runtime
     from open3dsot_b200.config import load_config
@@ -359,6 +385,8 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    if args.kernel_table:
+        kernel_table(eng, resident, args.kernel_table)
     roof = roofline_probe(dev, args.batch)
     roof_gather = gather_roofline(dev, args.batch)
     cb = None

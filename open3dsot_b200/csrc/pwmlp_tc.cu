@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
 //   tile [32 positions x 128 channels]:  atom(cb, pq) at (cb + 4*pq) * 512,  cb = channel/32, pq = position/4
 //   descriptor for k-step ks (8 positions = 2 atoms along K): start = tile + ks*4096,
 //   LBO = 512 (next 32-channel block), SBO = 2048 (next 4 positions)
-constexpr int WG_THREADS = 512;
+constexpr int WG_THREADS = 640;   // warps: 0 MMA | 1 L2 prefetch | 2,3 idle | 4-11 dY producers (4-7 also epilogue) | 12-19 X producers
 constexpr int WG_SMEM = TC_STAGES * STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
@@ -633,26 +633,26 @@ __device__ __forceinline__ uint32_t sw128_mn(int p_local, int c4) {   // c4 = fl
 template <class L, class KPos>
 __device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int tile_off, uint64_t* full, uint64_t* empty,
                                               int pt, int c_base, int CH, KPos kpos, int pend, int nkb, int dbg) {
-    const int c4 = pt & 31, prow0 = pt >> 5;      // rows prow0 + 4*i
+    const int c4 = pt & 31, prow0 = pt >> 5;      // 256 threads per operand: rows prow0 + 8*i, i < 4
     const int ch0 = c_base + c4 * 4;
     const typename L::Coef cf = ld.prep(ch0, CH);
-    typename L::template Batch<8> raw = {};
+    typename L::template Batch<4> raw = {};
     int stage = 0, phase = 0;
-    if (nkb > 0 && !(dbg & 2)) ld.fetch(raw, kpos(0) + prow0, 4, pend, ch0, CH);
+    if (nkb > 0 && !(dbg & 2)) ld.fetch(raw, kpos(0) + prow0, 8, pend, ch0, CH);
     for (int kb = 0; kb < nkb; ++kb) {
         o3d_mbar_wait(empty + stage, phase ^ 1);
         uint8_t* hi = smem + stage * STAGE_BYTES + tile_off;
         uint8_t* lo = hi + TILE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 v = ld.finish(raw, cf, i, kpos(kb) + prow0 + 4 * i, pend);
-            const uint32_t off = sw128_mn(prow0 + 4 * i, c4);
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = ld.finish(raw, cf, i, kpos(kb) + prow0 + 8 * i, pend);
+            const uint32_t off = sw128_mn(prow0 + 8 * i, c4);
             *reinterpret_cast<float4*>(hi + off) = hi_part(v);
             *reinterpret_cast<float4*>(lo + off) = lo_part(v);
         }
         o3d_fence_proxy_async();
         o3d_mbar_arrive(full + stage);
-        if (kb + 1 < nkb && !(dbg & 2)) ld.fetch(raw, kpos(kb + 1) + prow0, 4, pend, ch0, CH);
+        if (kb + 1 < nkb && !(dbg & 2)) ld.fetch(raw, kpos(kb + 1) + prow0, 8, pend, ch0, CH);
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
     }
 }
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            o3d_mbar_init(full + s, 256);
+            o3d_mbar_init(full + s, 512);
             o3d_mbar_init(empty + s, 1);
         }
         o3d_mbar_init(tfull, 1);
@@ -746,8 +746,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
                 paced_prefetch(da, xb, pbeg, pend, progress);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        if (nkb > 0) {
+    } else if (warp >= 4) {
+        // producers, 16 warps: 4-11 -> A (dY, channels m0..), 12-19 -> B (X, channels n0..); each thread owns 4 of a
+        // k-block's 32 rows.  (One warp per scheduler and operand could not issue the split + swizzled stores fast enough.)
+        const int pt = (threadIdx.x - 128) & 255;
+        if (warp < 12) wgrad_produce(da, smem, 0, full, empty, pt, m0, M, kpos, pend, nkb, dbg);
+        else wgrad_produce(xb, smem, 2 * TILE_BYTES, full, empty, pt, n0, N, kpos, pend, nkb, dbg);
+        if (warp < 8 && nkb > 0) {   // epilogue: warps 4-7 own TMEM lane quadrants 0-3
             const int q = warp & 3;
             const int ch = m0 + q * 32 + lane;
             o3d_mbar_wait(tfull, 0);
@@ -766,11 +771,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
                 }
             }
         }
-    } else if (warp >= 8) {
-        // producers: warps 8-11 -> A (dY, channels m0..), warps 12-15 -> B (X, channels n0..)
-        const int pt = (threadIdx.x - 256) & 127;
-        if (warp < 12) wgrad_produce(da, smem, 0, full, empty, pt, m0, M, kpos, pend, nkb, dbg);
-        else wgrad_produce(xb, smem, 2 * TILE_BYTES, full, empty, pt, n0, N, kpos, pend, nkb, dbg);
     }
     tc_fence_before();
     __syncthreads();
