@@ -660,10 +660,11 @@ __device__ __forceinline__ void wgrad_produce(const L& ld, uint8_t* smem, int ti
 
 // L2 prefetch of one CTA's slice of position rows, paced by the MMA warp's progress (rows consumed, published in shared
 // memory): at most WINDOW rows ahead.  Prefetching the whole slice up front asks for several hundred MB across the grid —
-// more than the 126 MB L2 — and the lines are evicted again before their k-block comes up.
+// more than the 126 MB L2 — and the lines are evicted again before their k-block comes up (measured: DRAM reads 1.7x the
+// algorithmic bytes with a 384-row window, L2 hit rate 11 %).
 template <class LA, class LB>
 __device__ __forceinline__ void paced_prefetch(const LA& da, const LB& xb, int pbeg, int pend, volatile int* progress) {
-    constexpr int CH = 128, WINDOW = 3 * CH;
+    constexpr int CH = 32, WINDOW = 4 * CH;   // 148 CTAs x 3 operands x 128 rows x <= 1 KB stays well inside the L2
     int issued = pbeg;
     while (issued < pend) {
         const int target = pbeg + *progress + WINDOW;
