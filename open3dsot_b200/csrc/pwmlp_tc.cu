@@ -175,22 +175,21 @@ struct TcDy {
     }
     template <int R>
     __device__ __forceinline__ void fetch(Batch<R>& bt, int p0, int stride, int P, int k, int K) const {
-        static_assert(R >= 2, "a batch holds the two pooled-gradient tables in g[0], g[1]");
         const int kk = k < K ? k : 0;
         bt.shared = false;
         if (dpool) {
             const int pf = p0 < P ? p0 : P - 1;
             const int pe = p0 + (R - 1) * stride;
             const int pl = pe < P ? pe : P - 1;
-            if ((pf >> sh) == (pl >> sh)) {
+            if (R >= 2 && (pf >> sh) == (pl >> sh)) {   // the two tables live in g[0], g[1]
                 bt.shared = true;
                 const size_t go = (size_t)(pf >> sh) * ldp + kk;
                 if (!(dbg & 256)) {
                     bt.g[0] = ld4g(dpool + go);
                     const int4 sl = __ldg(reinterpret_cast<const int4*>(sel + go));
-                    bt.g[1] = make_float4(__int_as_float(sl.x), __int_as_float(sl.y), __int_as_float(sl.z), __int_as_float(sl.w));
+                    bt.g[R >= 2 ? 1 : 0] = make_float4(__int_as_float(sl.x), __int_as_float(sl.y), __int_as_float(sl.z), __int_as_float(sl.w));
                 } else {
-                    bt.g[0] = bt.g[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bt.g[0] = bt.g[R >= 2 ? 1 : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             } else {
 #pragma unroll
@@ -222,7 +221,7 @@ struct TcDy {
         float4 v = bt.g[i];
         if (bt.shared) {
             const int s = p & (S - 1);
-            const float4 d = bt.g[0], sl = bt.g[1];
+            const float4 d = bt.g[0], sl = bt.g[R >= 2 ? 1 : 0];
             v = make_float4(__float_as_int(sl.x) == s ? d.x : 0.f, __float_as_int(sl.y) == s ? d.y : 0.f,
                             __float_as_int(sl.z) == s ? d.z : 0.f, __float_as_int(sl.w) == s ? d.w : 0.f);
         }
@@ -262,6 +261,7 @@ struct TcFwdEpi {
         mx = -INFINITY; mn = INFINITY; ax = an = 0;
     }
     __device__ __forceinline__ void prefetch(int, int, int, int) {}
+    __device__ __forceinline__ void prefetch_rows(int, int, int, int, int, int) const {}
     // Fast path = a full group of 16 positions that lies inside one pooling group (S >= 16, the set-abstraction case):
     // no per-element range or group-boundary test, the max / min / first-arg scan is local to the 16 values and is merged
     // into the running (mx, ax, mn, an) of the pooling group with two compares.  Everything else takes the element-wise path.
@@ -345,6 +345,16 @@ struct TcDgradEpi {
         d1 = d2 = 0.0;
         sc = (scale && ch < Nw) ? scale[ch] : 1.f;
         sh = (shift && ch < Nw) ? shift[ch] : 0.f;
+    }
+    // the epilogue's own operand (raw outputs of the previous layer, channels ch0 .. ch0+nch of rows p0 ..) -> L2, one tile ahead
+    __device__ __forceinline__ void prefetch_rows(int ch0, int nch, int Nw, int p0, int rows, int P) const {
+        if (!yprev || p0 >= P || ch0 >= Nw) return;
+        const int n = min(rows, P - p0), w = min(nch, Nw - ch0);
+        if (w == ldyp) {
+            o3d_prefetch_l2(yprev + (size_t)p0 * ldyp, (size_t)n * ldyp * sizeof(float));
+        } else {
+            for (int r = 0; r < n; ++r) o3d_prefetch_l2(yprev + (size_t)(p0 + r) * ldyp + ch0, (size_t)w * sizeof(float));
+        }
     }
     // issue the previous layer's raw outputs for this column group before waiting on TMEM (independent loads)
     __device__ __forceinline__ void prefetch(int ch, int Nw, int pbase, int P) {
@@ -499,10 +509,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         // ===================================================== weight-tile streamer (bulk copy engine)
         if (lane == 0) {
             int stage = 0, phase = 0;
-            if (!(dbg & 8) && (int)blockIdx.x < n_ptiles) bl.prefetch_rows(tile_of(blockIdx.x) * TC_N, TC_N, P);
+            if (!(dbg & 8) && (int)blockIdx.x < n_ptiles) {
+                bl.prefetch_rows(tile_of(blockIdx.x) * TC_N, TC_N, P);
+                epi.prefetch_rows(mt0 * TC_M, MT * TC_M, Nw, tile_of(blockIdx.x) * TC_N, TC_N, P);
+            }
             for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
-                if (!(dbg & 8) && t + (int)gridDim.x < n_ptiles)
+                if (!(dbg & 8) && t + (int)gridDim.x < n_ptiles) {
                     bl.prefetch_rows(tile_of(t + (int)gridDim.x) * TC_N, TC_N, P);   // next tile of this CTA -> L2
+                    epi.prefetch_rows(mt0 * TC_M, MT * TC_M, Nw, tile_of(t + (int)gridDim.x) * TC_N, TC_N, P);
+                }
                 for (int kb = 0; kb < nkb; ++kb) {
                     o3d_mbar_wait(empty + stage, phase ^ 1);
                     if ((dbg & 1) && t != (int)blockIdx.x) {
@@ -791,7 +806,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 //   descriptor (channel half h, k-step ks): start = tile + h*2048 + ks*2*SBO, LBO = 512, SBO = 4*H*512
 constexpr int WG2_K = 16;
 constexpr int WG2_STAGES = 3;
-constexpr int WG2_THREADS = 576;   // warps: 0 MMA | 1 prefetch | 2,3,12-17 producers | 4-11 epilogue
+constexpr int WG2_THREADS = 576;   // warps: 0 MMA | 1 prefetch | 2-17 producers (4-11 also run the epilogue)
 
 template <int MH, int NH> struct Wg2Cfg {
     static constexpr int A_BYTES = WG2_K * 128 * MH * 4;            // one of hi / lo
@@ -837,7 +852,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WG2_STAGES; ++s) {
-            o3d_mbar_init(full + s, 256);
+            o3d_mbar_init(full + s, 512);
             o3d_mbar_init(empty + s, 1);
         }
         o3d_mbar_init(tfull, 1);
@@ -892,43 +907,13 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
                 paced_prefetch(da, xb, pbeg, pend, progress);
             }
         }
-    } else if (warp >= 4 && warp < 12) {
-        // epilogue: partial tile -> workspace part[split][m][n] (plain coalesced stores; zeros when this slice is empty)
-        const int q = warp & 3, grp = (warp - 4) >> 2;                 // grp 0: warps 4-7, 1: warps 8-11
-        const int Mt = 128 * MH * (int)gridDim.z, Nt = 128 * NH * (int)gridDim.y;
-        float* __restrict__ out = part + (size_t)blockIdx.x * Mt * Nt;
-        if (nkb > 0) {
-            o3d_mbar_wait(tfull, 0);
-            tc_fence_after();
-        }
-        for (int t = grp; t < MH * NH; t += 2) {                       // accumulators shared between the two warp groups
-            const int mh = t / NH, nh = t % NH;
-            const int row = m0 + mh * 128 + q * 32 + lane;
-            float* __restrict__ orow = out + (size_t)row * Nt + n0 + nh * 128;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 128);
-#pragma unroll 1
-            for (int cg = 0; cg < 8; ++cg) {
-                uint32_t r[16];
-                if (nkb > 0) {
-                    tmem_ld16(taddr + cg * 16, r);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = 0u;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(orow + cg * 16 + j) =
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            }
-        }
     } else {
-        // producers (8 warps): every thread serves both operands, raw loads first
-        const int pw = warp < 4 ? warp - 2 : warp - 10;
-        const int pt = pw * 32 + lane;                                  // 0..255
+        // producers (16 warps, 2-17): every thread serves both operands, raw loads first
+        const int pt = threadIdx.x - 64;                                // 0..511
         constexpr int CA = 32 * MH, CB = 32 * NH;                       // float4 per position row
-        constexpr int RA = WG2_K * CA / 256, RB = WG2_K * CB / 256;     // float4 per thread per stage (2 or 4)
-        const int ca4 = pt % CA, pa0 = pt / CA, sa = 256 / CA;          // A: rows pa0 + sa*i
-        const int cb4 = pt % CB, pb0 = pt / CB, sbs = 256 / CB;
+        constexpr int RA = WG2_K * CA / 512, RB = WG2_K * CB / 512;     // float4 per thread per stage (1 or 2)
+        const int ca4 = pt % CA, pa0 = pt / CA, sa = 512 / CA;          // A: rows pa0 + sa*i
+        const int cb4 = pt % CB, pb0 = pt / CB, sbs = 512 / CB;
         const TcDy::Coef cfa = da.prep(m0 + ca4 * 4, M);
         const TcAct::Coef cfb = xb.prep(n0 + cb4 * 4, N);
         TcDy::Batch<RA> ra = {};
@@ -966,6 +951,36 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
             o3d_mbar_arrive(full + stage);
             if (kb + 1 < nkb) fetch(kb + 1);
             if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (warp >= 4 && warp < 12) {
+            // epilogue: partial tile -> workspace part[split][m][n] (plain coalesced stores; zeros when this slice is empty)
+            const int q = warp & 3, grp = (warp - 4) >> 2;                 // grp 0: warps 4-7, 1: warps 8-11
+            const int Mt = 128 * MH * (int)gridDim.z, Nt = 128 * NH * (int)gridDim.y;
+            float* __restrict__ out = part + (size_t)blockIdx.x * Mt * Nt;
+            if (nkb > 0) {
+                o3d_mbar_wait(tfull, 0);
+                tc_fence_after();
+            }
+            for (int t = grp; t < MH * NH; t += 2) {                       // accumulators shared between the two warp groups
+                const int mh = t / NH, nh = t % NH;
+                const int row = m0 + mh * 128 + q * 32 + lane;
+                float* __restrict__ orow = out + (size_t)row * Nt + n0 + nh * 128;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 128);
+    #pragma unroll 1
+                for (int cg = 0; cg < 8; ++cg) {
+                    uint32_t r[16];
+                    if (nkb > 0) {
+                        tmem_ld16(taddr + cg * 16, r);
+                    } else {
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = 0u;
+                    }
+    #pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(orow + cg * 16 + j) =
+                            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+            }
         }
     }
     tc_fence_before();
