@@ -521,6 +521,90 @@ __global__ void __launch_bounds__(NT, 2)
     }
 }
 
+// Forward layer with a handful of input columns (an xyz-only first layer, K <= 8) and no pooling: the tiled kernel spends
+// its time on empty k-tiles, this one is a single streaming pass — thread = (4 output channels, every R-th position), the
+// K x 4 weight block lives in registers, rows are stored as coalesced float4, batch statistics go through registers ->
+// shared memory -> one fp64 RED per channel and block.
+template <int KQ>
+__global__ void __launch_bounds__(256, 2)
+    pw_fwd_skinny_kernel(ActIn ain, const float* __restrict__ Wt, int ldw, int P, int K, int Nw, int LQ, int chunk, FwdEpi ep) {
+    __shared__ float red[2][256 * 4];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.y * 256;
+    const int cq = tid % LQ, r = tid / LQ, R = 256 / LQ;
+    const int n = n0 + cq * 4;
+    const bool on = n < Nw;
+    float4 w[4 * KQ];
+#pragma unroll
+    for (int k = 0; k < 4 * KQ; ++k) w[k] = (on && k < K) ? ld4(Wt + (size_t)k * ldw + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bv = (on && ep.bias) ? ld4(ep.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
+    constexpr int U = 4;
+    for (int p = pbeg + r; p < pend; p += U * R) {
+        ActRaw x[U][KQ];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < KQ; ++q) x[u][q] = fetch_act(ain, p + u * R, pend, q * 4, K);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pp = p + u * R;
+            if (pp >= pend || !on) continue;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < KQ; ++q) {
+                const float4 xv = finish_act(ain, x[u][q], pp, pend, q * 4, K);
+                const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 ww = w[q * 4 + j];
+                    acc.x = fmaf(xx[j], ww.x, acc.x); acc.y = fmaf(xx[j], ww.y, acc.y);
+                    acc.z = fmaf(xx[j], ww.z, acc.z); acc.w = fmaf(xx[j], ww.w, acc.w);
+                }
+            }
+            acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+            if (ep.y) *reinterpret_cast<float4*>(ep.y + (size_t)pp * ep.ldy + n) = acc;
+            s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
+            s2.x = fmaf(acc.x, acc.x, s2.x); s2.y = fmaf(acc.y, acc.y, s2.y);
+            s2.z = fmaf(acc.z, acc.z, s2.z); s2.w = fmaf(acc.w, acc.w, s2.w);
+        }
+    }
+    if (!ep.sum) return;
+    for (int i = tid; i < 2 * 256 * 4; i += 256) (&red[0][0])[i] = 0.f;
+    __syncthreads();
+    if (on) {
+        const float a1[4] = {s1.x, s1.y, s1.z, s1.w}, a2[4] = {s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            atomicAdd(&red[0][cq * 4 + i], a1[i]);
+            atomicAdd(&red[1][cq * 4 + i], a2[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 256; i += 256) {
+        if (n0 + i < Nw) {
+            atomicAdd(ep.sum + n0 + i, (double)red[0][i]);
+            atomicAdd(ep.sumsq + n0 + i, (double)red[1][i]);
+        }
+    }
+}
+
+template <int KQ>
+int launch_fwd_skinny(const ActIn& ain, const float* wt, int ldw, int P, int K, int Nw, const FwdEpi& ep, cudaStream_t st) {
+    const int slabs = (Nw + 255) / 256;
+    const int mq = (std::min(Nw, 256) + 3) / 4;
+    const int LQ = mq <= 16 ? 16 : (mq <= 32 ? 32 : 64);
+    const int R = 256 / LQ;
+    int want = (4 * o3d_num_sms() + slabs - 1) / slabs;
+    int chunk = (P + want - 1) / want;
+    chunk = ((chunk + 4 * R - 1) / (4 * R)) * (4 * R);
+    const int nx = (P + chunk - 1) / chunk;
+    pw_fwd_skinny_kernel<KQ><<<dim3(nx, slabs), 256, 0, st>>>(ain, wt, ldw, P, K, Nw, LQ, chunk, ep);
+    O3D_CHECK_LAUNCH("o3d_pw_fwd (skinny)");
+    return O3D_OK;
+}
+
 // wgrad for a handful of input columns — an xyz-only first layer, or the (dx, dy, dz, 0) / box-cloud extras behind the
 // tensor-core part of a first layer:  dW[m, n] += sum_p dY[p, m] * A(X)[p, n],  n < 4*NQ <= 12.
 // No tiles: one streaming pass over dY (the only operand of any size), thread = (4 output channels, every R-th position),
@@ -673,24 +757,53 @@ __global__ void pool_finalize_kernel(const float* __restrict__ ymax, const float
     if (ysel) ysel[o] = y;
 }
 
+// Row-streaming helpers of the two "prep" kernels below: block = 128 channels x 4 row lanes, every thread walks its rows
+// four at a time (independent loads first), the 4 row lanes are combined through shared memory, one fp64 RED per channel
+// and block.
+constexpr int PREP_LANES = 4, PREP_UNROLL = 4;
+__device__ __forceinline__ void prep_reduce(float t1, float t2, int c, int C, double* s1, double* s2y) {
+    __shared__ float red[2][PREP_LANES][128];
+    red[0][threadIdx.y][threadIdx.x] = t1;
+    red[1][threadIdx.y][threadIdx.x] = t2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int l = 0; l < PREP_LANES; ++l) { a += red[0][l][threadIdx.x]; b += red[1][l][threadIdx.x]; }
+        if (s1) atomicAdd(s1 + c, (double)a);
+        if (s2y) atomicAdd(s2y + c, (double)b);
+    }
+}
+
 // backward of the pooled activation: dpool = dout * [out > 0] (if relu); column sums of dpool and dpool*ysel
-__global__ void pool_bwd_prep_kernel(const float* __restrict__ dout, int ldd, const float* __restrict__ out, int ldo,
-                                     const float* __restrict__ ysel, int relu, int G, int C, int ldp,
-                                     float* __restrict__ dpool, double* __restrict__ s1, double* __restrict__ s2y) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+__global__ void __launch_bounds__(128 * PREP_LANES)
+    pool_bwd_prep_kernel(const float* __restrict__ dout, int ldd, const float* __restrict__ out, int ldo,
+                         const float* __restrict__ ysel, int relu, int G, int C, int ldp, float* __restrict__ dpool,
+                         double* __restrict__ s1, double* __restrict__ s2y) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int cc = c < C ? c : C - 1;
     float t1 = 0.f, t2 = 0.f;
-    for (int g = blockIdx.y; g < G; g += gridDim.y) {
-        float d = dout[(size_t)g * ldd + c];
-        if (relu && !(out[(size_t)g * ldo + c] > 0.f)) d = 0.f;
-        dpool[(size_t)g * ldp + c] = d;
-        t1 += d;
-        t2 = fmaf(d, ysel[(size_t)g * ldp + c], t2);
+    const int step = gridDim.y * PREP_LANES;
+    for (int g0 = blockIdx.y * PREP_LANES + threadIdx.y; g0 < G; g0 += step * PREP_UNROLL) {
+        float d[PREP_UNROLL], o[PREP_UNROLL], ys[PREP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PREP_UNROLL; ++u) {
+            const int g = min(g0 + u * step, G - 1);
+            d[u] = dout[(size_t)g * ldd + cc];
+            o[u] = relu ? out[(size_t)g * ldo + cc] : 1.f;
+            ys[u] = ysel[(size_t)g * ldp + cc];
+        }
+#pragma unroll
+        for (int u = 0; u < PREP_UNROLL; ++u) {
+            const int g = g0 + u * step;
+            if (g >= G || c >= C) continue;
+            const float v = (relu && !(o[u] > 0.f)) ? 0.f : d[u];
+            dpool[(size_t)g * ldp + c] = v;
+            t1 += v;
+            t2 = fmaf(v, ys[u], t2);
+        }
     }
-    if (s1) {
-        atomicAdd(s1 + c, (double)t1);
-        atomicAdd(s2y + c, (double)t2);
-    }
+    prep_reduce(t1, t2, c, C, s1, s1 ? s2y : nullptr);
 }
 
 // dense activation (no pooling): out = act(scale*y + shift)
@@ -708,22 +821,34 @@ __global__ void act_apply_kernel(const float* __restrict__ y, int ldy, const flo
 }
 
 // dense backward prep: g = dout * [out > 0] (if relu); column sums of g and g*y (y nullable -> only s1)
-__global__ void dense_bwd_prep_kernel(const float* __restrict__ dout, int ldd, const float* __restrict__ out, int ldo,
-                                      const float* __restrict__ y, int ldy, int relu, int P, int C,
-                                      float* __restrict__ g, int ldg, double* __restrict__ s1,
-                                      double* __restrict__ s2y) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+__global__ void __launch_bounds__(128 * PREP_LANES)
+    dense_bwd_prep_kernel(const float* __restrict__ dout, int ldd, const float* __restrict__ out, int ldo,
+                          const float* __restrict__ y, int ldy, int relu, int P, int C, float* __restrict__ g, int ldg,
+                          double* __restrict__ s1, double* __restrict__ s2y) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int cc = c < C ? c : C - 1;
     float t1 = 0.f, t2 = 0.f;
-    for (int p = blockIdx.y; p < P; p += gridDim.y) {
-        float d = dout[(size_t)p * ldd + c];
-        if (relu && !(out[(size_t)p * ldo + c] > 0.f)) d = 0.f;
-        if (g) g[(size_t)p * ldg + c] = d;
-        t1 += d;
-        if (y) t2 = fmaf(d, y[(size_t)p * ldy + c], t2);
+    const int step = gridDim.y * PREP_LANES;
+    for (int p0 = blockIdx.y * PREP_LANES + threadIdx.y; p0 < P; p0 += step * PREP_UNROLL) {
+        float d[PREP_UNROLL], o[PREP_UNROLL], yy[PREP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PREP_UNROLL; ++u) {
+            const int p = min(p0 + u * step, P - 1);
+            d[u] = dout[(size_t)p * ldd + cc];
+            o[u] = relu ? out[(size_t)p * ldo + cc] : 1.f;
+            yy[u] = y ? y[(size_t)p * ldy + cc] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < PREP_UNROLL; ++u) {
+            const int p = p0 + u * step;
+            if (p >= P || c >= C) continue;
+            const float v = (relu && !(o[u] > 0.f)) ? 0.f : d[u];
+            if (g) g[(size_t)p * ldg + c] = v;
+            t1 += v;
+            t2 = fmaf(v, yy[u], t2);
+        }
     }
-    if (s1) atomicAdd(s1 + c, (double)t1);
-    if (s2y) atomicAdd(s2y + c, (double)t2);
+    prep_reduce(t1, t2, c, C, s1, s2y);
 }
 
 template <typename Kern>
@@ -757,6 +882,10 @@ extern "C" int o3d_pw_fwd(const float* x, int ldx, const float* in_scale, const 
     ActIn ain{x, ldx, in_scale, in_shift, in_relu};
     FwdEpi ep{y, ldy, bias, sum, sumsq, S, ymax, ymin, arg, ldp};
     cudaStream_t st = (cudaStream_t)stream;
+    if (K <= 8 && S == 0 && P >= 4096 && !o3d_g_no_skinny) {
+        if (K <= 4) return launch_fwd_skinny<1>(ain, wt, ldw, P, K, Nw, ep, st);
+        return launch_fwd_skinny<2>(ain, wt, ldw, P, K, Nw, ep, st);
+    }
     if (Nw <= 64) {
         if (int e = set_smem(pw_fwd_kernel<64>, Cfg<64>::SMEM_BYTES, "o3d_pw_fwd")) return e;
         dim3 grid((P + BM - 1) / BM, (Nw + 63) / 64);
@@ -882,10 +1011,12 @@ extern "C" int o3d_pool_bwd_prep(const float* dout, int ldd, const float* out, i
                                  int G, int C, int ldp, float* dpool, double* s1, double* s2y, void* stream) {
     O3D_REQUIRE(dout && out && ysel && dpool, O3D_ERR_ARG, "o3d_pool_bwd_prep: null pointer");
     if (G == 0) return O3D_OK;
-    int gy = (G + 63) / 64;
-    if (gy > 1024) gy = 1024;
+    int gy = (G + PREP_LANES * PREP_UNROLL - 1) / (PREP_LANES * PREP_UNROLL);   // one unrolled pass per thread ...
+    const int cap = 4 * o3d_num_sms() / ((C + 127) / 128);                       // ... up to ~4 blocks per SM
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
     dim3 grid((C + 127) / 128, gy);
-    pool_bwd_prep_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(dout, ldd, out, ldo, ysel, relu, G, C, ldp, dpool, s1,
+    pool_bwd_prep_kernel<<<grid, dim3(128, PREP_LANES), 0, (cudaStream_t)stream>>>(dout, ldd, out, ldo, ysel, relu, G, C, ldp, dpool, s1,
                                                                   s2y);
     O3D_CHECK_LAUNCH("o3d_pool_bwd_prep");
     return O3D_OK;
@@ -907,10 +1038,12 @@ extern "C" int o3d_dense_bwd_prep(const float* dout, int ldd, const float* out, 
     O3D_REQUIRE(dout, O3D_ERR_ARG, "o3d_dense_bwd_prep: null pointer");
     O3D_REQUIRE(!relu || out, O3D_ERR_ARG, "o3d_dense_bwd_prep: relu mask needs the forward output");
     if (P == 0) return O3D_OK;
-    int gy = (P + 63) / 64;
-    if (gy > 2048) gy = 2048;
+    int gy = (P + PREP_LANES * PREP_UNROLL - 1) / (PREP_LANES * PREP_UNROLL);
+    const int cap = 4 * o3d_num_sms() / ((C + 127) / 128);
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
     dim3 grid((C + 127) / 128, gy);
-    dense_bwd_prep_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(dout, ldd, out, ldo, y, ldy, relu, P, C, g, ldg, s1,
+    dense_bwd_prep_kernel<<<grid, dim3(128, PREP_LANES), 0, (cudaStream_t)stream>>>(dout, ldd, out, ldo, y, ldy, relu, P, C, g, ldg, s1,
                                                                    s2y);
     O3D_CHECK_LAUNCH("o3d_dense_bwd_prep");
     return O3D_OK;

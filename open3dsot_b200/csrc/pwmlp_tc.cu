@@ -351,7 +351,6 @@ struct TcDgradEpi {
     // issue the previous layer's raw outputs for this column group before waiting on TMEM (independent loads)
     __device__ __forceinline__ void prefetch(int ch, int Nw, int pbase, int P) {
         if (!yprev || ch >= Nw) return;
-#pragma unroll
         if (pbase + 16 <= P) {
             const float* yp = yprev + (size_t)pbase * ldyp + ch;
             const size_t st = LD ? (size_t)LD : (size_t)ldyp;
