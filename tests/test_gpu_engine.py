@@ -55,11 +55,13 @@ def test_graph_replay_matches_eager_steps():
         la.append(float(eager.step(b)))
         lb.append(float(graph.step(b)))
     assert graph.graph is not None                           # the last steps really were replays
-    # step 2 is the first replay: same state, same batch -> same loss up to the summation order of the fp32 REDs.
-    # Afterwards the two runs are two samples of the same round-off-chaotic trajectory (4-pair batches, Adam, discrete
-    # neighbourhoods): only closeness of the first replayed steps is a meaningful check.
-    assert abs(la[1] - lb[1]) <= 1e-4 * abs(la[1]), (la, lb)
-    assert abs(la[2] - lb[2]) <= 2e-2 * abs(la[2]), (la, lb)
+    # step 1 is eager in both engines: identical loss.  Step 2 is the first replay: same batch, state equal up to the
+    # summation order of the fp32 REDs in step 1's weight gradients — which is already enough to flip a discrete choice
+    # (proposal top-k, ball query on predicted centres) in a 4-pair batch.  From there on the two runs are two samples of
+    # the same round-off-chaotic trajectory: only closeness of the first replayed steps is a meaningful check.
+    assert abs(la[0] - lb[0]) <= 1e-6 * abs(la[0]), (la, lb)
+    assert abs(la[1] - lb[1]) <= 2e-2 * abs(la[1]), (la, lb)
+    assert abs(la[2] - lb[2]) <= 6e-2 * abs(la[2]), (la, lb)
     assert all(0.3 * x < y < 3.0 * x for x, y in zip(la, lb)), (la, lb)
 
 
