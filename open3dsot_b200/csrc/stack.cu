@@ -39,10 +39,24 @@ __device__ __forceinline__ uint32_t tile_sw128(int r, int c) {
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-__global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int cin, int Nw, int K, int xyz_first, int c0,
-                                   float* __restrict__ wp, float* __restrict__ wt, const float* __restrict__ bias,
-                                   float* __restrict__ bias_p, uint8_t* __restrict__ tiles_f, uint8_t* __restrict__ tiles_b,
-                                   int Km /* input channels tiled for dgrad */, int Npad, int Kpad /* iteration space */) {
+struct PackLayer {
+    const float* src; const float* bias; float* wp; float* wt; float* bias_p; uint8_t* tiles_f; uint8_t* tiles_b;
+    int cout, cin, Nw, K, xyz_first, Km /* input channels tiled for dgrad */, Npad, Kpad /* iteration space */;
+};
+struct PackArgs { PackLayer l[O3D_MAX_LAYERS]; int c0; };
+
+// all layers of a stack in one launch: blockIdx.y = layer
+__global__ void pack_weight_kernel(const PackArgs args) {
+    const PackLayer& L = args.l[blockIdx.y];
+    const float* __restrict__ src = L.src;
+    const float* __restrict__ bias = L.bias;
+    float* __restrict__ wp = L.wp;
+    float* __restrict__ wt = L.wt;
+    float* __restrict__ bias_p = L.bias_p;
+    uint8_t* __restrict__ tiles_f = L.tiles_f;
+    uint8_t* __restrict__ tiles_b = L.tiles_b;
+    const int cout = L.cout, cin = L.cin, Nw = L.Nw, K = L.K, xyz_first = L.xyz_first, c0 = args.c0, Km = L.Km, Npad = L.Npad,
+              Kpad = L.Kpad;
     constexpr int TILE = 128 * 32 * 4;
     const int nkb_f = (K + 31) / 32;
     const int k4n = Kpad / 4;
@@ -84,10 +98,17 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int 
     }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int cout, int cin, int K, int xyz_first, int c0,
-                                    float* __restrict__ dst) {
+struct UnpackLayer { const float* dwp; float* dst; int cout, cin, K, xyz_first; };
+struct UnpackArgs { UnpackLayer l[O3D_MAX_LAYERS]; int c0; };
+
+// padded / re-ordered weight gradients -> the checkpoint layout, all layers of a stack in one launch (blockIdx.y = layer)
+__global__ void unpack_wgrad_kernel(const UnpackArgs args) {
+    const UnpackLayer& L = args.l[blockIdx.y];
+    const float* __restrict__ dwp = L.dwp;
+    float* __restrict__ dst = L.dst;
+    const int cout = L.cout, cin = L.cin, K = L.K, xyz_first = L.xyz_first, c0 = args.c0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cout * K) return;
+    if (!dst || i >= cout * K) return;
     const int n = i / K, k = i % K;
     const int sc = src_col(k, K, cin, xyz_first, c0);
     if (sc >= 0) dst[(size_t)n * cin + sc] = dwp[i];
@@ -192,6 +213,32 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* ws = (uint8_t*)ws_fwd;
     O3D_CUDA(cudaMemsetAsync(ws + p.stat_all, 0, p.stat_bytes, st), "o3d_stack_forward: memset");   // statistics + BN vectors
+    {   // every layer's padded weights, transposes, bias and pre-tiled images: one launch
+        PackArgs pa{};
+        pa.c0 = d->c0;
+        int work_max = 0;
+        for (int l = 0; l < p.n; ++l) {
+            const int Nw = p.Nw[l], K = p.K[l];
+            PackLayer& q = pa.l[l];
+            q.src = d->weight[l]; q.bias = d->bias[l];
+            q.wp = at<float>(ws, p.wp[l]); q.wt = at<float>(ws, p.wt[l]);
+            q.bias_p = d->bias[l] ? at<float>(ws, p.bias[l]) : nullptr;
+            q.tiles_f = p.tc_f[l] ? ws + p.tiles[l] : nullptr;
+            q.tiles_b = (p.tc_b[l] && keep_for_backward) ? ws + p.btiles[l] : nullptr;
+            q.cout = d->cout[l]; q.cin = d->cin[l]; q.Nw = Nw; q.K = K; q.xyz_first = l == 0 ? d->xyz_first : 0;
+            q.Km = tc_main(K);
+            q.Npad = Nw; q.Kpad = K;
+            if (q.tiles_f) { q.Npad = ((Nw + 127) / 128) * 128; q.Kpad = ((K + 31) / 32) * 32; }
+            if (q.tiles_b) {
+                if (q.Npad < ((Nw + 31) / 32) * 32) q.Npad = ((Nw + 31) / 32) * 32;
+                if (q.Kpad < ((q.Km + 127) / 128) * 128) q.Kpad = ((q.Km + 127) / 128) * 128;
+            }
+            const int work = q.Npad * (q.Kpad / 4);
+            if (work > work_max) work_max = work;
+        }
+        pack_weight_kernel<<<dim3((work_max + 255) / 256, p.n), 256, 0, st>>>(pa);
+        O3D_CHECK_LAUNCH("o3d_stack_forward: pack_weight");
+    }
     const float* cur = x;
     int cur_ld = d->K0;
     const float *in_scale = nullptr, *in_shift = nullptr;
@@ -199,25 +246,8 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
     const int L = p.n - 1;
     for (int l = 0; l < p.n; ++l) {
         const int Nw = p.Nw[l], K = p.K[l], cout = d->cout[l];
-        float* wp = at<float>(ws, p.wp[l]);
         float* wt = at<float>(ws, p.wt[l]);
         float* bias = d->bias[l] ? at<float>(ws, p.bias[l]) : nullptr;
-        {
-            uint8_t* tf = p.tc_f[l] ? ws + p.tiles[l] : nullptr;
-            uint8_t* tb = (p.tc_b[l] && keep_for_backward) ? ws + p.btiles[l] : nullptr;
-            const int Km = tc_main(K);
-            int Npad = Nw, Kpad = K;
-            if (tf) { Npad = ((Nw + 127) / 128) * 128; Kpad = ((K + 31) / 32) * 32; }
-            if (tb) {
-                if (Npad < ((Nw + 31) / 32) * 32) Npad = ((Nw + 31) / 32) * 32;
-                if (Kpad < ((Km + 127) / 128) * 128) Kpad = ((Km + 127) / 128) * 128;
-            }
-            const int work = Npad * (Kpad / 4);
-            pack_weight_kernel<<<(work + 255) / 256, 256, 0, st>>>(d->weight[l], cout, d->cin[l], Nw, K,
-                                                                   l == 0 ? d->xyz_first : 0, d->c0, wp, wt, d->bias[l], bias,
-                                                                   tf, tb, Km, Npad, Kpad);
-        }
-        O3D_CHECK_LAUNCH("o3d_stack_forward: pack_weight");
         const bool last = l == L, pool = last && p.S > 0;
         const bool keep_y = !last || keep_for_backward || !pool;
         float* y = keep_y ? at<float>(ws, p.y[l]) : nullptr;
@@ -380,8 +410,20 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
                 rc = o3d_pw_wgrad(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, xin, K, psc, psh, prelu, p.P, Nl, K, dwp, K, stream);
             }
             if (rc) return rc;
-            unpack_wgrad_kernel<<<(cout * K + 255) / 256, 256, 0, st>>>(dwp, cout, d->cin[l], K, l == 0 ? d->xyz_first : 0,
-                                                                        d->c0, d->d_weight[l]);
+        }
+    }
+    {
+        UnpackArgs ua{};
+        ua.c0 = d->c0;
+        int work_max = 0;
+        for (int l = 0; l < p.n; ++l) {
+            UnpackLayer& q = ua.l[l];
+            q.dwp = at<float>(wb, p.dwp[l]); q.dst = d->d_weight[l];
+            q.cout = d->cout[l]; q.cin = d->cin[l]; q.K = p.K[l]; q.xyz_first = l == 0 ? d->xyz_first : 0;
+            if (q.dst && q.cout * q.K > work_max) work_max = q.cout * q.K;
+        }
+        if (work_max > 0) {
+            unpack_wgrad_kernel<<<dim3((work_max + 255) / 256, p.n), 256, 0, st>>>(ua);
             O3D_CHECK_LAUNCH("o3d_stack_backward: unpack_wgrad");
         }
     }

@@ -79,7 +79,7 @@ def test_full_size_step_fused_vs_composed():
             loss = net.training_step({k: v.clone() for k, v in batch.items()}, 0)
             loss.backward()
             g = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
-            res[fused_mode] = (float(loss), g)
+            res[fused_mode] = (float(loss.detach()), g)
             assert torch.isfinite(loss) and torch.isfinite(g).all()
         finally:
             runtime.set_fused(True)
