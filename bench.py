@@ -187,6 +187,18 @@ def gather_roofline(dev, batch_pairs):
             "algorithmic_bytes_per_launch": alg_bytes}
 
 
+def ncu_traffic(P):
+    """DRAM bytes per launch of the roofline kernel as ncu measured them (dram__bytes_read.sum + dram__bytes_write.sum of
+    one `--set full` capture of the same kernel and shape, committed under profiles/); None when the shape differs."""
+    path = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f)
+        return float(rec["dram_bytes_per_launch"]) if f"P={P}," in rec["shape"] else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def roofline_probe(dev, batch_pairs):
     """The dominant kernel family of the step — the point-wise MLP GEMM (pw_tc_kernel, forward, SA3-search layer:
     196608 positions x 256 -> 256 channels) — timed alone with CUDA events on its stream through the C ABI.
@@ -234,7 +246,7 @@ def roofline_probe(dev, batch_pairs):
             "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
             "frac": (tf / tensor_peak) if bound == "tensor" else (gbs / peaks["hbm_gbs"]),
             "peak_source": how + " MEASURED_PEAKS.json: bf16_tflops/2/3 (TF32 rate, three passes) and hbm_gbs (burst)",
-            "traffic": None, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
+            "traffic": ncu_traffic(P), "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
             "algorithmic_bytes_per_launch": alg_bytes, "achieved_tflops_fp32_equiv": tf, "achieved_gbs": gbs,
             "frac_of_tensor_roof": tf / tensor_peak, "frac_of_hbm_roof": gbs / peaks["hbm_gbs"]}
 
