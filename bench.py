@@ -251,6 +251,59 @@ def roofline_probe(dev, batch_pairs):
             "frac_of_tensor_roof": tf / tensor_peak, "frac_of_hbm_roof": gbs / peaks["hbm_gbs"]}
 
 
+def roofline_backward_probe(dev, batch_pairs):
+    """The two backward GEMMs on the SA2-search shape (393216 positions, 128 -> 128 channels, BN + ReLU on both sides),
+    each timed alone through the C ABI.  At 128 channels both are HBM-bound: dgrad reads g, y and the previous layer's raw
+    output (for the ReLU mask) and writes the input gradient; wgrad reads g, y and the layer input."""
+    from open3dsot_b200 import _lib
+    L = _lib.lib()
+    P, C = max(batch_pairs, 48) * 256 * 32, 128
+    g = torch.randn(P, C, device=dev) * 1e-3
+    y = torch.randn(P, C, device=dev)
+    yprev = torch.randn(P, C, device=dev)
+    out = torch.empty(P, C, device=dev)
+    w = torch.randn(C, C, device=dev) * 0.05
+    a, b, cc = (torch.rand(C, device=dev) + 0.5), torch.randn(C, device=dev) * 1e-4, torch.randn(C, device=dev) * 1e-4
+    sc, sh = (torch.rand(C, device=dev) + 0.5), torch.randn(C, device=dev) * 0.1
+    stat = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    dw = torch.zeros(C, C, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    wt = w.t().contiguous()
+    tiles = torch.empty(int(L.o3d_pw_tc_wtile_bytes(C, C)), dtype=torch.uint8, device=dev)
+    _lib.check(L.o3d_pw_tc_pretile(wt.data_ptr(), C, C, C, tiles.data_ptr(), st), "pretile")
+
+    def dgrad():
+        _lib.check(L.o3d_pw_dgrad_tc(g.data_ptr(), C, y.data_ptr(), C, a.data_ptr(), b.data_ptr(), cc.data_ptr(), None, None, 0, 0,
+                                     tiles.data_ptr(), P, C, C, out.data_ptr(), C, yprev.data_ptr(), C, sc.data_ptr(),
+                                     sh.data_ptr(), 1, stat.data_ptr(), stat.data_ptr() + 8 * C, st), "o3d_pw_dgrad_tc")
+
+    def wgrad():
+        _lib.check(L.o3d_pw_wgrad_tc(g.data_ptr(), C, y.data_ptr(), C, a.data_ptr(), b.data_ptr(), cc.data_ptr(), None, None, 0, 0,
+                                     yprev.data_ptr(), C, sc.data_ptr(), sh.data_ptr(), 1, P, C, C, dw.data_ptr(), C, st),
+                   "o3d_pw_wgrad_tc")
+    peaks, how = measured_peaks()
+    res = []
+    for name, fn, nbytes in (("pw_tc_kernel<1,TcDy,TcDgradEpi<128>> (dgrad)", dgrad, 4.0 * P * C * 4),
+                             ("pw_wgrad_tc_kernel (wgrad)", wgrad, 4.0 * P * C * 3)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        n = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res.append({"kernel": name + ", SA2-search layer: P=%d, 128 -> 128 channels" % P, "bound": "hbm", "achieved": gbs,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                    "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
+                    "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"})
+    return res
+
+
 def kernel_table(eng, batches, path, steps=3):
     """Per-kernel device time of `steps` training steps as CUPTI records them (activity tracing: no replay, no
     serialisation beyond the step's own stream order).  Not a bench value: tracing adds a little launch overhead."""
@@ -401,6 +454,7 @@ def run_ours(args):
         kernel_table(eng, resident, args.kernel_table)
     roof = roofline_probe(dev, args.batch)
     roof_gather = gather_roofline(dev, args.batch)
+    roof_bwd = roofline_backward_probe(dev, args.batch)
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(args.cpu_batch, args.cpu_steps)
@@ -419,7 +473,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": launches, "wall_s_timed_region": wall,
             "e2e": {"value": pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / args.steps * 1e3},
-            "roofline": roof, "roofline_gather": roof_gather, "cpu_baseline": cb}
+            "roofline": roof, "roofline_gather": roof_gather, "roofline_backward": roof_bwd, "cpu_baseline": cb}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

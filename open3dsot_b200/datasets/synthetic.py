@@ -172,3 +172,26 @@ def synthetic_motion_batch(batch_size, point_sample_size=1024, seed=20260924, wl
     if device != "cpu":
         batch = {k: v.to(device, non_blocking=True) for k, v in batch.items()}
     return batch
+
+
+def synthetic_sequence(n_frames=8, n_points=20000, seed=20260924, wlh=CAR_WLH, speed=0.6, yaw_rate=2.0, n_object=600):
+    """A synthetic tracklet with the schema of the reference's test datasets (datasets/kitti.py:150-205:
+    a list of {"pc": PointCloud (3, N), "3d_bbox": Box}): one car-sized box driving along a gently curved path through
+    ground + clutter returns.  Frame i: centre advances `speed` m along its heading, heading turns `yaw_rate` degrees."""
+    from .data_classes import Box, PointCloud
+    rng = np.random.default_rng(seed)
+    center, yaw = np.array([8.0, 2.0, -0.8 + wlh[2] / 2]), np.deg2rad(15.0)
+    ground = np.stack([rng.uniform(-10, 40, n_points), rng.uniform(-20, 20, n_points), np.full(n_points, -0.8)], 1)
+    clutter = rng.uniform([-10, -20, -0.8], [40, 20, 2.0], size=(n_points // 10, 3))
+    frames = []
+    for _ in range(n_frames):
+        c, s = np.cos(yaw), np.sin(yaw)
+        rot = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+        obj = _surface_points(rng, n_object, wlh) @ rot.T + center[None]
+        bg = np.concatenate([ground + rng.normal(0, 0.01, ground.shape), clutter])
+        bg = bg[~_in_box(bg, center, np.asarray(wlh) * 1.05, yaw)]
+        pts = np.concatenate([obj, bg[: n_points - n_object]]).astype(np.float32)
+        frames.append({"pc": PointCloud(pts.T.copy()), "3d_bbox": Box(center.copy(), wlh, rot.copy())})
+        center = center + speed * np.array([c, s, 0.0])
+        yaw = yaw + np.deg2rad(yaw_rate)
+    return frames

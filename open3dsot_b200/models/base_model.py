@@ -1,11 +1,39 @@
-"""Model base classes.  Mirror of the training-relevant part of models/base_model.py: BaseModel
-(optimizer/scheduler, :28-36) and MatchingBaseModel.compute_loss (:122-164).  The tracking evaluation loop
-(:44-117, :166-247) needs the dataset stack (nuscenes-devkit, shapely, pyquaternion) and is out of scope for
-the hot path."""
+"""Model base classes.  Mirror of models/base_model.py: BaseModel (optimizer/scheduler :28-36, the tracking frame loop
+:44-86), MatchingBaseModel (compute_loss :122-164, template / search-area construction :166-247).
+The frame loop keeps the reference's method names and control flow but runs its geometry as tensor math on the model's
+device (open3dsot_b200/tracking/boxes.py) instead of numpy + pyquaternion on the host; `tracking.DeviceTracker` is the
+fixed-shape, graph-captured form of the same loop."""
+import numpy as np
 import torch
 import torch.nn.functional as F
 
 from ..compat import EasyDict, LightningModule
+from ..datasets import data_classes
+from ..tracking import boxes as bx
+from ..utils.metrics import estimateAccuracy, estimateOverlap
+
+
+def _points(pc, device):
+    """(N, 3) float32 tensor on `device` from a PointCloud-like object (`.points` (3, N)) or an (N, 3) array / tensor."""
+    pts = getattr(pc, "points", pc)
+    t = torch.as_tensor(np.asarray(pts) if not torch.is_tensor(pts) else pts, dtype=torch.float32, device=device)
+    return t.t().contiguous() if (t.shape[0] == 3 and t.shape[-1] != 3) or hasattr(pc, "points") else t
+
+
+def _tbox(box, device):
+    return box if isinstance(box, bx.Box) else data_classes.Box(box.center, box.wlh, box.rotation_matrix).to_tensor(device)
+
+
+def regularize(points, sample_size, seed=None):
+    """points_utils.regularize_pc (:24-40) on an (N, 3) tensor: the index draw is the reference's numpy Generator."""
+    n = points.shape[0]
+    if n <= 2:
+        return torch.zeros(sample_size, 3, dtype=points.dtype, device=points.device), None
+    if n == sample_size:
+        return points, np.arange(n)
+    rng = np.random if seed is None else np.random.default_rng(seed)
+    idx = rng.choice(n, size=sample_size, replace=sample_size > n)
+    return points[torch.as_tensor(idx, device=points.device)], idx
 
 
 class BaseModel(LightningModule):
@@ -29,8 +57,35 @@ class BaseModel(LightningModule):
     def compute_loss(self, data, output):
         raise NotImplementedError
 
+    def build_input_dict(self, sequence, frame_id, results_bbs, **kwargs):
+        raise NotImplementedError
+
+    def evaluate_one_sample(self, data_dict, ref_box):
+        """:44-60: run the network, take the best proposal, move the reference box by it (getOffsetBB)."""
+        with torch.no_grad():
+            end_points = self(data_dict)
+        est = end_points['estimation_boxes'][0]
+        if est.dim() == 2:
+            est = est.index_select(0, est[:, 4].argmax().reshape(1))[0, :4]    # (indexing by a 0-d tensor would sync)
+        ref = _tbox(ref_box, self.device)
+        new = bx.offset_box(ref, est.to(ref.center.dtype), degrees=self.config.degrees, use_z=self.config.use_z,
+                            limit_box=self.config.limit_box)
+        return data_classes.Box.from_tensor(new)
+
     def evaluate_one_sequence(self, sequence):
-        raise NotImplementedError("tracking evaluation needs the dataset stack; out of scope for the hot path")
+        """:62-86.  sequence: list of {"pc": PointCloud, "3d_bbox": Box}; returns (ious, distances, result boxes)."""
+        ious, distances, results_bbs = [], [], []
+        for frame_id in range(len(sequence)):
+            this_bb = sequence[frame_id]["3d_bbox"]
+            if frame_id == 0:
+                results_bbs.append(this_bb)
+            else:
+                data_dict, ref_bb = self.build_input_dict(sequence, frame_id, results_bbs)
+                results_bbs.append(self.evaluate_one_sample(data_dict, ref_box=ref_bb))
+            ious.append(estimateOverlap(this_bb, results_bbs[-1], dim=self.config.IoU_space, up_axis=self.config.up_axis))
+            distances.append(estimateAccuracy(this_bb, results_bbs[-1], dim=self.config.IoU_space,
+                                              up_axis=self.config.up_axis))
+        return ious, distances, results_bbs
 
 
 class MatchingBaseModel(BaseModel):
@@ -59,6 +114,58 @@ class MatchingBaseModel(BaseModel):
                                     box_label[:, None, :4].expand_as(estimation_boxes[:, :, :4]), reduction='none')
         loss_box = torch.sum(loss_box.mean(2) * objectness_label) / (objectness_label.sum() + 1e-6)
         return {"loss_objective": loss_objective, "loss_box": loss_box, "loss_seg": loss_seg, "loss_vote": loss_vote}
+
+
+    # ---- tracking input construction (:166-247) ----------------------------------------------------------------
+    def _crop_and_center(self, pc, box):
+        pts = _points(pc, self.device)
+        local, keep, canon = bx.crop_and_center(pts, _tbox(box, self.device), offset=self.config.model_bb_offset,
+                                                scale=self.config.model_bb_scale)
+        return local[keep], canon
+
+    def generate_template(self, sequence, current_frame_id, results_bbs):
+        mode = self.config.shape_aggregation.upper()
+        first_pc, previous_pc = sequence[0]['pc'], sequence[current_frame_id - 1]['pc']
+        if "FIRSTANDPREVIOUS" in mode:
+            pairs = [(first_pc, results_bbs[0]), (previous_pc, results_bbs[current_frame_id - 1])]
+        elif "FIRST" in mode:
+            pairs = [(first_pc, results_bbs[0])]
+        elif "PREVIOUS" in mode:
+            pairs = [(previous_pc, results_bbs[current_frame_id - 1])]
+        elif "ALL" in mode:
+            pairs = [(f["pc"], b) for f, b in zip(sequence[:current_frame_id], results_bbs)]
+        else:
+            raise ValueError(self.config.shape_aggregation)
+        parts, canon = [], None
+        for pc, box in pairs:                      # getModel (:88-100): merged crops, canonical box of the last pair
+            pts, canon = self._crop_and_center(pc, box)
+            parts.append(pts)
+        return torch.cat(parts), canon
+
+    def generate_search_area(self, sequence, current_frame_id, results_bbs):
+        ref = self.config.reference_BB.upper()
+        if "PREVIOUS_RESULT" in ref:
+            ref_bb = results_bbs[-1]
+        elif "PREVIOUS_GT" in ref:
+            ref_bb = sequence[current_frame_id - 1]["3d_bbox"]
+        elif "CURRENT_GT" in ref:
+            ref_bb = sequence[current_frame_id]["3d_bbox"]
+        else:
+            raise ValueError(self.config.reference_BB)
+        pts = _points(sequence[current_frame_id]["pc"], self.device)
+        local, keep = bx.subwindow(pts, _tbox(ref_bb, self.device), scale=self.config.search_bb_scale,
+                                   offset=self.config.search_bb_offset)
+        return local[keep], ref_bb
+
+    def prepare_input(self, template_pc, search_pc, template_box, *args, **kwargs):
+        template_points, _ = regularize(template_pc, self.config.template_size, seed=1)
+        search_points, _ = regularize(search_pc, self.config.search_size, seed=1)
+        return {'template_points': template_points[None], 'search_points': search_points[None]}
+
+    def build_input_dict(self, sequence, frame_id, results_bbs, **kwargs):
+        search_pc_crop, ref_bb = self.generate_search_area(sequence, frame_id, results_bbs)
+        template_pc, canonical_box = self.generate_template(sequence, frame_id, results_bbs)
+        return self.prepare_input(template_pc, search_pc_crop, canonical_box), ref_bb
 
 
 class MotionBaseModel(BaseModel):

@@ -29,6 +29,16 @@ class BAT(base_model.MatchingBaseModel):
         self.rpn = P2BVoteNetRPN(c.feature_channel, vote_channel=c.vote_channel, num_proposal=c.num_proposal,
                                  normalize_xyz=c.normalize_xyz)
 
+    def prepare_input(self, template_pc, search_pc, template_box):
+        """bat.py:41-55: the matching models' input plus the template's BoxCloud (distances to centre + 8 corners)."""
+        from ..tracking import boxes as bx
+        from .base_model import regularize
+        template_points, _ = regularize(template_pc, self.config.template_size, seed=1)
+        search_points, _ = regularize(search_pc, self.config.search_size, seed=1)
+        template_bc = bx.point_to_box_distance(template_points, template_box)
+        return {'template_points': template_points[None], 'search_points': search_points[None],
+                'points2cc_dist_t': template_bc[None]}
+
     def compute_loss(self, data, output):
         out_dict = super().compute_loss(data, output)
         seg_label = data['seg_label']

@@ -1,0 +1,33 @@
+"""Fixed-shape resampling of a masked point set — the device-side form of points_utils.regularize_pc (:24-40).
+
+The reference draws `numpy.random.default_rng(seed=1).choice(n, size, replace=size > n)` on the host, which needs the
+number of surviving points on the host (a device->host sync per crop) and a host RNG.  Here the candidates stay a
+fixed-size array plus a keep-mask and the draw is expressed with sorts and gathers of fixed shape, so a whole frame
+(crop, resample, model, box update) can be captured in one CUDA graph:
+  * n >= size : `size` distinct survivors, uniformly at random (sort by random keys, survivors first);
+  * 2 < n < size : `size` draws with replacement;
+  * n <= 2 : all-zero cloud (the reference's "too few points" placeholder).
+The subset differs from the numpy Generator's (same distribution); tests that compare against the host restatement pass
+the oracle's indices through `indices=`."""
+import torch
+
+
+def resample(points, keep, size, generator=None, indices=None, u_perm=None, u_pick=None):
+    """points (N, 3), keep (N,) bool -> (size, 3) points, (size,) source indices (into `points`).
+    `u_perm` (N,) / `u_pick` (size,): uniform [0, 1) draws supplied by the caller (static buffers refreshed outside a
+    captured graph, which keeps a replayed frame reproducible from a seed); drawn here when absent."""
+    n_all = points.shape[0]
+    if indices is not None:                                   # explicit indices INTO THE SURVIVORS, in their order
+        order = torch.nonzero(keep, as_tuple=False)[:, 0]
+        src = order[indices]
+        return points[src], src
+    n = keep.sum()
+    u = torch.rand(n_all, device=points.device, generator=generator) if u_perm is None else u_perm
+    order = torch.argsort(torch.where(keep, u, torch.full_like(u, 2.0)))          # survivors first, random order
+    if n_all < size:
+        order = torch.cat([order, order.new_zeros(size - n_all)])
+    up = torch.rand(size, device=points.device, generator=generator) if u_pick is None else u_pick
+    pick = (up * n).long().clamp_(max=torch.clamp(n - 1, min=0))
+    src = torch.where(n >= size, order[:size], order[pick])
+    out = points[src]
+    return torch.where(n > 2, out, torch.zeros_like(out)), src

@@ -1,0 +1,227 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) for the B=1 tracking-inference path of SURVEY.md §8(f) rank 2: the geometry the
+reference's frame loop runs on the host between two model calls.
+
+PARITY UNPINNED: the reference functions live in datasets/points_utils.py / datasets/data_classes.py / utils/metrics.py and
+need pyquaternion, shapely, nuscenes-devkit and torchmetrics, none of which is installed here, so they cannot be executed
+to produce golden vectors.  This file restates their arithmetic with plain numpy, one function per reference function, each
+citing the lines it follows; orientations are carried as 3x3 rotation matrices (pyquaternion is only used upstream to
+compose and invert rotations: `Quaternion(matrix=M)` == M, `.inverse` == M.T, `q1 * q2` == M1 @ M2,
+`Quaternion(axis=[0,0,1], degrees=a)` == rotz(a)), and polygon clipping replaces shapely for the two convex
+quadrilaterals of a bird's-eye-view IoU.
+
+Only tests/ may import this module."""
+import copy
+
+import numpy as np
+
+
+def rotz(angle, degrees=True):
+    a = np.deg2rad(angle) if degrees else angle
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+
+
+class Box:
+    """center (3,), wlh (3,), rot (3,3).  datasets/data_classes.py:128-257 with the quaternion replaced by its matrix."""
+
+    def __init__(self, center, wlh, rot):
+        self.center = np.array(center, dtype=np.float64)
+        self.wlh = np.array(wlh, dtype=np.float64)
+        self.rot = np.array(rot, dtype=np.float64)
+
+    def translate(self, x):                       # data_classes.py:205-211
+        self.center = self.center + np.asarray(x, dtype=np.float64)
+
+    def rotate(self, m):                          # data_classes.py:213-221  (q * orientation, centre rotated too)
+        self.center = m @ self.center
+        self.rot = m @ self.rot
+
+    def corners(self, wlh_factor=1.0):            # data_classes.py:229-252: x forward (l), y left (w), z up (h)
+        w, l, h = self.wlh * wlh_factor
+        x = l / 2 * np.array([1, 1, 1, 1, -1, -1, -1, -1])
+        y = w / 2 * np.array([1, -1, -1, 1, 1, -1, -1, 1])
+        z = h / 2 * np.array([1, 1, -1, -1, 1, 1, -1, -1])
+        return self.rot @ np.vstack((x, y, z)) + self.center[:, None]
+
+    def bottom_corners(self):                     # data_classes.py:254-257
+        return self.corners()[:, [2, 3, 7, 6]]
+
+
+def regularize_pc(points, sample_size, seed=None):
+    """points_utils.py:24-40 (numpy Generator.choice when a seed is given, as the evaluation loop does with seed=1)."""
+    n = points.shape[0]
+    idx = None
+    rng = np.random if seed is None else np.random.default_rng(seed)
+    if n > 2:
+        idx = rng.choice(n, size=sample_size, replace=sample_size > n) if n != sample_size else np.arange(n)
+    if idx is not None:
+        return points[idx, :], idx
+    return np.zeros((sample_size, 3), dtype="float32"), None
+
+
+def get_offset_bb(box, offset, degrees=True, use_z=False, limit_box=True, rng=np.random):
+    """points_utils.py:43-85.  Net effect: centre += R @ (dx, dy, dz*use_z), R <- R @ rotz(angle)."""
+    offset = np.array(offset, dtype=np.float64)
+    new_box = copy.deepcopy(box)
+    rot, trans = box.rot.copy(), box.center.copy()
+    new_box.translate(-trans)
+    new_box.rotate(rot.T)
+    if len(offset) == 3:
+        use_z = False
+    ang = offset[2] if len(offset) == 3 else offset[3]
+    new_box.rotate(rotz(ang, degrees))
+    if limit_box:
+        if offset[0] > new_box.wlh[0]:
+            offset[0] = rng.uniform(-1, 1)
+        if offset[1] > min(new_box.wlh[1], 2):
+            offset[1] = rng.uniform(-1, 1)
+        if use_z and offset[2] > new_box.wlh[2]:
+            offset[2] = 0
+    new_box.translate(np.array([offset[0], offset[1], offset[2] if use_z else 0.0]))
+    new_box.rotate(rot)
+    new_box.translate(trans)
+    return new_box
+
+
+def crop_pc_axis_aligned(points, box, offset=0, scale=1.0):
+    """points_utils.py:147-173 on a (3, N) array; strict inequalities."""
+    tmp = copy.deepcopy(box)
+    tmp.wlh = tmp.wlh * scale
+    c = tmp.corners()
+    maxi, mini = c.max(1) + offset, c.min(1) - offset
+    keep = np.ones(points.shape[1], dtype=bool)
+    for a in range(3):
+        keep &= (points[a] > mini[a]) & (points[a] < maxi[a])
+    return points[:, keep], keep
+
+
+def crop_and_center_pc(points, box, offset=0, scale=1.0):
+    """points_utils.py:102-124: coarse world-frame crop (4x scale, 2x offset), move into the box frame, exact crop."""
+    pts, _ = crop_pc_axis_aligned(points, box, offset=2 * offset, scale=4 * scale)
+    new_box = copy.deepcopy(box)
+    rot_t, trans = box.rot.T.copy(), -box.center
+    pts = rot_t @ (pts + trans[:, None])
+    new_box.translate(trans)
+    new_box.rotate(rot_t)
+    pts, _ = crop_pc_axis_aligned(pts, new_box, offset=offset, scale=scale)
+    return pts, new_box
+
+
+def get_model(pcs, boxes, offset=0, scale=1.0):
+    """points_utils.py:88-100: merged canonical template; the returned box is the one of the LAST pair."""
+    parts = [np.ones((3, 0))]
+    new_box = None
+    for pts, box in zip(pcs, boxes):
+        cropped, new_box = crop_and_center_pc(pts, box, offset=offset, scale=scale)
+        if cropped.shape[1] > 0:
+            parts.append(cropped)
+    return np.concatenate(parts, axis=1), new_box
+
+
+def generate_subwindow(points, box, scale, offset=2):
+    """points_utils.py:223-254, oriented=True: points in the frame of `box`, cropped to its scaled + padded extent."""
+    tmp = copy.deepcopy(box)
+    rot_t, trans = box.rot.T.copy(), -box.center
+    pts = rot_t @ (points + trans[:, None])
+    tmp.translate(trans)
+    tmp.rotate(rot_t)
+    out, _ = crop_pc_axis_aligned(pts, tmp, scale=scale, offset=offset)
+    return out
+
+
+def get_point_to_box_distance(points, box, wlh_factor=1.0):
+    """points_utils.py:127-144: (N, 9) distances to the centre and the 8 corners (the BoxCloud)."""
+    ref = np.concatenate([box.center.reshape(3, 1), box.corners(wlh_factor)], axis=1).T     # (9, 3)
+    return np.sqrt(((points[:, None, :] - ref[None, :, :]) ** 2).sum(-1))
+
+
+# ---- metrics (utils/metrics.py) ---------------------------------------------------------------------------------
+def _clip(subject, clipper):
+    """Sutherland-Hodgman: convex `subject` polygon clipped by convex `clipper`, both counter-clockwise (k, 2)."""
+    out = [tuple(p) for p in subject]
+    for i in range(len(clipper)):
+        a, b = clipper[i], clipper[(i + 1) % len(clipper)]
+        inp, out = out, []
+        if not inp:
+            break
+
+        def inside(p):
+            return (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0]) >= 0
+
+        def cross(p, q):
+            d1, d2 = (p[0] - q[0], p[1] - q[1]), (a[0] - b[0], a[1] - b[1])
+            den = d1[0] * d2[1] - d1[1] * d2[0]
+            n1, n2 = p[0] * q[1] - p[1] * q[0], a[0] * b[1] - a[1] * b[0]
+            return ((n1 * d2[0] - d1[0] * n2) / den, (n1 * d2[1] - d1[1] * n2) / den)
+        s = inp[-1]
+        for e in inp:
+            if inside(e):
+                if not inside(s):
+                    out.append(cross(s, e))
+                out.append(e)
+            elif inside(s):
+                out.append(cross(s, e))
+            s = e
+    return np.array(out).reshape(-1, 2)
+
+
+def _area(poly):
+    if len(poly) < 3:
+        return 0.0
+    x, y = poly[:, 0], poly[:, 1]
+    return 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+
+
+def _ccw(poly):
+    x, y = poly[:, 0], poly[:, 1]
+    return poly if (np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1))) > 0 else poly[::-1]
+
+
+def box_to_poly(box, up_axis=(0, -1, 0)):
+    """utils/metrics.py:37-47."""
+    if up_axis[1] != 0:
+        return box.corners()[[0, 2]].T[[0, 1, 5, 4]]
+    return box.bottom_corners().T[:, :2]      # shapely ignores the third coordinate for areas
+
+
+def estimate_overlap(box_a, box_b, dim=2, up_axis=(0, -1, 0)):
+    """utils/metrics.py:50-74."""
+    pa, pb = _ccw(box_to_poly(box_a, up_axis)), _ccw(box_to_poly(box_b, up_axis))
+    inter = _area(_clip(pa, pb))
+    union = _area(pa) + _area(pb) - inter
+    if dim == 2:
+        return inter / union if union > 0 else 0.0      # degenerate footprint: shapely raises, the reference returns 0
+    up = np.array(up_axis) != 0
+    up_max = min(box_a.center[up], box_b.center[up])
+    up_min = max(box_a.center[up] - box_a.wlh[2], box_b.center[up] - box_b.wlh[2])
+    inter_vol = inter * max(0, up_max[0] - up_min[0])
+    va, vb = np.prod(box_a.wlh), np.prod(box_b.wlh)
+    return inter_vol / (va + vb - inter_vol)
+
+
+def estimate_accuracy(box_a, box_b, dim=3, up_axis=(0, -1, 0)):
+    """utils/metrics.py:27-34."""
+    if dim == 3:
+        return np.linalg.norm(box_a.center - box_b.center)
+    keep = np.array(up_axis) != 0
+    return np.linalg.norm(box_a.center[keep] - box_b.center[keep])
+
+
+def success(overlaps, n=21, max_overlap=1.0):
+    """utils/metrics.py:104-128: area under the success curve, in percent."""
+    xs = np.linspace(0, max_overlap, n)
+    o = np.asarray(overlaps, dtype=np.float64)
+    if o.size == 0:
+        return 0.0
+    ys = np.array([(o >= t).mean() for t in xs])
+    return float(np.trapezoid(ys, xs) * 100 / max_overlap)
+
+
+def precision(accs, n=21, max_accuracy=2.0):
+    """utils/metrics.py:77-101."""
+    xs = np.linspace(0, max_accuracy, n)
+    a = np.asarray(accs, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    ys = np.array([(a <= t).mean() for t in xs])
+    return float(np.trapezoid(ys, xs) * 100 / max_accuracy)
