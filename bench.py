@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--fused", type=int, default=None, help="override O3D_FUSED (1 = fused kernels, 0 = composed)")
     ap.add_argument("--tc", type=int, default=None, help="override O3D_TC (0 = CUDA cores, 1 = tcgen05 fwd+dgrad, 3 = + wgrad)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
+    ap.add_argument("--track", action="store_true", help="secondary mode: B=1 tracking frames/s (SURVEY.md 8f rank 2)")
+    ap.add_argument("--track-points", type=int, default=60000, help="points per synthetic scan in --track mode")
     ap.add_argument("--kernel-table", default=None, metavar="FILE",
                     help="also write the per-kernel device times of 3 steps (CUPTI, no replay, warm caches) to FILE")
     ap.add_argument("--cfg", default=None, help="other config to exercise (P2B_Car.yaml, M2_track_kitti.yaml, ...): a parity / "
@@ -125,6 +127,97 @@ def cpu_baseline(batch_pairs, steps, seed=20260924):
     return {"value": batch_pairs / med, "unit": "pairs/s", "cores": cores, "kind": "port",
             "sample": f"oracle BAT fwd+bwd, batch {batch_pairs} pairs of 512/1024 pts, median of {steps} steps after 1 warm-up",
             "ms_per_step": med * 1e3}
+
+
+def track_cpu_baseline(cfg, seq, frames):
+    """The reference's frame as it runs on the host: numpy crop / resample / BoxCloud / box update (oracle/tracking_ref.py)
+    around the oracle's eval-mode forward on the CPU (oracle/modules.py)."""
+    import numpy as np
+    from open3dsot_b200.models import get_model
+    from oracle import modules as om
+    from oracle import tracking_ref as tr
+    cores = min(os.cpu_count() or 1, 16)
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = get_model(cfg.net_model)(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    fwd = om.bat_forward if cfg.net_model.lower() == "bat" else om.p2b_forward
+    boxes = [tr.Box(seq[0]["3d_bbox"].center, seq[0]["3d_bbox"].wlh, seq[0]["3d_bbox"].rotation_matrix)]
+    times = []
+    for i in range(1, min(frames, len(seq))):
+        t0 = time.perf_counter()
+        ref = boxes[-1]
+        search = tr.generate_subwindow(seq[i]["pc"].points.astype(np.float64), ref, cfg.search_bb_scale, cfg.search_bb_offset)
+        tmpl, canon = tr.get_model([seq[0]["pc"].points.astype(np.float64), seq[i - 1]["pc"].points.astype(np.float64)],
+                                   [boxes[0], ref], offset=cfg.model_bb_offset, scale=cfg.model_bb_scale)
+        tp, _ = tr.regularize_pc(tmpl.T, cfg.template_size, seed=1)
+        sp, _ = tr.regularize_pc(search.T, cfg.search_size, seed=1)
+        batch = {"template_points": torch.tensor(tp, dtype=torch.float32)[None], "search_points": torch.tensor(sp, dtype=torch.float32)[None]}
+        if cfg.net_model.lower() == "bat":
+            batch["points2cc_dist_t"] = torch.tensor(tr.get_point_to_box_distance(tp, canon), dtype=torch.float32)[None]
+        with torch.no_grad():
+            out = fwd(sd, cfg, batch, False)
+        est = out["estimation_boxes"][0].numpy()
+        est = est[est[:, 4].argmax(), :4]
+        boxes.append(tr.get_offset_bb(ref, est, degrees=cfg.degrees, use_z=cfg.use_z, limit_box=cfg.limit_box))
+        if i > 1:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": 1.0 / med, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"numpy frame geometry + oracle {cfg.net_model} eval forward, B=1, median of {len(times)} frames", "ms_per_frame": med * 1e3}
+
+
+def run_track(args):
+    """Secondary mode: B=1 tracking frames/s on a synthetic tracklet — the reference-shaped host loop,
+    the fixed-shape device frame, and the same frame replayed from one CUDA graph; CPU baseline beside it."""
+    from open3dsot_b200.config import load_config
+    from open3dsot_b200.datasets.synthetic import synthetic_sequence
+    from open3dsot_b200.models import get_model
+    from open3dsot_b200.tracking.device_tracker import DeviceTracker
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    cfg = load_config(CFG_FILE if args.cfg is None else os.path.join(ROOT, "cfgs", args.cfg), {"up_axis": [0, 0, 1]})
+    torch.manual_seed(0)
+    net = get_model(cfg.net_model)(cfg).to(dev).eval()
+    frames, npts = max(args.steps + args.warmup + 1, 12), args.track_points
+    seq = synthetic_sequence(n_frames=frames, n_points=npts, seed=20260924)
+    pts = [torch.tensor(f["pc"].points.T.copy(), device=dev) for f in seq]
+    w = max(args.warmup, 3)
+    net.evaluate_one_sequence(seq[: w + 1])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    net.evaluate_one_sequence(seq)
+    torch.cuda.synchronize()
+    res = {"host_loop_fps": (frames - 1) / (time.perf_counter() - t0)}
+    sampler = ClockSampler(0)
+    sampler.start()
+    for name, graph in (("device_eager", False), ("device_graph", True)):
+        trk = DeviceTracker(net, max_points=npts, use_graph=graph)
+        trk.reset(pts[0], seq[0]["3d_bbox"].to_tensor(dev))
+        for i in range(1, w + 1):
+            trk.step(pts[i])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(w + 1, frames):
+            trk.step(pts[i])
+        e1.record()
+        torch.cuda.synchronize()
+        n = frames - w - 1
+        res[name + "_fps"] = n / max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
+        res[name + "_ms_device"] = e0.elapsed_time(e1) / n
+    clocks = sampler.stop()
+    cb = None if args.no_cpu_baseline else track_cpu_baseline(cfg, seq, 8)
+    print(json.dumps({"metric": f"tracking frames/sec, {cfg.net_model} B=1 (crop + resample + network + box update per frame)",
+                      "value": res["device_graph_fps"], "unit": "frames/s", "n_gpus": 1, "steps": frames - w - 1, "warmup": w,
+                      "ms_per_step": res["device_graph_ms_device"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"{os.path.basename(args.cfg or CFG_FILE)} tracking inference, synthetic tracklet, "
+                                             f"{npts} points per scan, template {cfg.template_size} / search {cfg.search_size}",
+                                 "l2": "every frame reads a different scan", "cuda_graph": True},
+                      "clocks": clocks, **res, "cpu_baseline": cb}))
 
 
 def run_reference(args):
@@ -483,5 +576,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.track:
+        run_track(a)
     else:
         run_ours(a)
