@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--tc", type=int, default=None, help="override O3D_TC (0 = CUDA cores, 1 = tcgen05 fwd+dgrad, 3 = + wgrad)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--track", action="store_true", help="secondary mode: B=1 tracking frames/s (SURVEY.md 8f rank 2)")
+    ap.add_argument("--sampler", action="store_true", help="secondary mode: on-device training-batch construction (8f rank 3)")
     ap.add_argument("--track-points", type=int, default=60000, help="points per synthetic scan in --track mode")
     ap.add_argument("--kernel-table", default=None, metavar="FILE",
                     help="also write the per-kernel device times of 3 steps (CUPTI, no replay, warm caches) to FILE")
@@ -218,6 +219,82 @@ def run_track(args):
                                              f"{npts} points per scan, template {cfg.template_size} / search {cfg.search_size}",
                                  "l2": "every frame reads a different scan", "cuda_graph": True},
                       "clocks": clocks, **res, "cpu_baseline": cb}))
+
+
+def sampler_cpu_baseline(cfg, tracklets, n_pairs=24):
+    """The reference's per-pair batch construction on one host core: the numpy restatement of siamese_processing."""
+    import numpy as np
+    from oracle import tracking_ref as tr
+    frames = [f for t in tracklets for f in t]
+    starts, k = [], 0
+    for t in tracklets:
+        starts += [k] * len(t)
+        k += len(t)
+    rng = np.random.default_rng(0)
+    deg = 5.0 if cfg.degrees else np.deg2rad(5.0)
+
+    def fr(f):
+        b = f["3d_bbox"]
+        return f["pc"].points.astype(np.float64), tr.Box(b.center, b.wlh, b.rotation_matrix)
+    t0 = time.perf_counter()
+    for i in range(n_pairs):
+        k = int(rng.integers(len(frames)))
+        prev = max(k - 1, starts[k])
+        tr.siamese_processing(fr(frames[starts[k]]), fr(frames[prev]), fr(frames[k]), i % cfg.get("num_candidates", 1), cfg,
+                              rng.uniform(-0.3, 0.3, 3), rng.normal(size=3) * np.sqrt([1.0, 1.0, deg]))
+    dt = time.perf_counter() - t0
+    return {"value": n_pairs / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+            "sample": f"numpy siamese_processing, {n_pairs} pairs, scans of {frames[0]['pc'].points.shape[1]} points, one core "
+                      f"(the reference runs one such worker per DataLoader process, 10 per GPU)", "ms_per_pair": dt / n_pairs * 1e3}
+
+
+def run_sampler(args):
+    """Secondary mode: training batches built on the device, alone and feeding the training step."""
+    from open3dsot_b200.config import load_config
+    from open3dsot_b200.datasets.device_sampler import DeviceSiameseSampler
+    from open3dsot_b200.datasets.synthetic import synthetic_sequence
+    from open3dsot_b200.engine import TrainStep
+    from open3dsot_b200.models import get_model
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    cfg = load_config(CFG_FILE if args.cfg is None else os.path.join(ROOT, "cfgs", args.cfg), {"batch_size": args.batch})
+    tracklets = [synthetic_sequence(n_frames=8, n_points=args.track_points, seed=20260924 + i) for i in range(6)]
+    smp = DeviceSiameseSampler(tracklets, cfg, dev, seed=1)
+    w, n = max(args.warmup, 3), args.steps
+    for _ in range(w):
+        batch, valid = smp.next_batch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        batch, valid = smp.next_batch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_sampler = e0.elapsed_time(e1) / n
+    torch.manual_seed(0)
+    net = get_model(cfg.net_model)(cfg).to(dev).train()
+    eng = TrainStep(net, lr=cfg.lr, weight_decay=cfg.wd, use_graph=True, warmup=2)
+    for _ in range(w + 3):
+        eng.step(smp.next_batch()[0])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0.record()
+    for _ in range(n):
+        loss = eng.step(smp.next_batch()[0])
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / n
+    clocks = sampler.stop()
+    cb = None if args.no_cpu_baseline else sampler_cpu_baseline(cfg, tracklets)
+    print(json.dumps({"metric": f"training pairs/sec with batches constructed on the device, {cfg.net_model}", "value": args.batch / ms_step * 1e3,
+                      "unit": "pairs/s", "n_gpus": 1, "steps": n, "warmup": w, "ms_per_step": ms_step, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"{os.path.basename(args.cfg or CFG_FILE)} train step fed by DeviceSiameseSampler: "
+                                             f"6 synthetic tracklets x 8 scans of {args.track_points} points resident on the device, "
+                                             f"batch {args.batch}", "l2": "every step builds a new batch from different frames"},
+                      "clocks": clocks, "sampler_ms_per_batch": ms_sampler, "sampler_pairs_per_s": args.batch / ms_sampler * 1e3,
+                      "last_loss": float(loss), "cpu_baseline": cb}))
 
 
 def run_reference(args):
@@ -578,5 +655,7 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.track:
         run_track(a)
+    elif a.sampler:
+        run_sampler(a)
     else:
         run_ours(a)

@@ -1,0 +1,139 @@
+"""On-device construction of siamese training batches.
+
+The reference builds every template-search pair on the host (datasets/sampler.py:16-79 `siamese_processing`, driven by
+`PointTrackingSampler.__getitem__` :213-243, ten DataLoader workers per GPU): numpy crops, pyquaternion box algebra, a
+Python call per pair.  At the rate the fused training step consumes pairs (thousands per second per GPU) that pipeline is
+the bottleneck, so here the tracklets live on the device as padded tensors and one call produces a whole batch with
+batched tensor math: frame selection, the two random box offsets, template = first-frame crop + offset previous-frame crop
+(getModel), search area = sub-window around the offset current box, segmentation labels, box regression target, fixed-shape
+resampling and the two BoxClouds.  Output keys, shapes and dtypes are those of the reference's collated batch.
+
+Samples the reference rejects (<= 20 template or search points: it catches the AssertionError and draws another index)
+are drawn here as an oversampled pool; the first `batch_size` valid ones are returned."""
+import torch
+
+from ..tracking import boxes as bx
+from ..tracking.sampling import resample_batched
+
+
+class DeviceTracklets:
+    """Tracklets as padded device tensors: scans (F, Nmax, 3) + valid counts (F,), one box per frame, and for every frame
+    the index of its tracklet's first frame and of its predecessor (clamped at the start: sampler.py:229-231)."""
+
+    def __init__(self, tracklets, device, max_points=None):
+        frames = [f for t in tracklets for f in t]
+        nmax = max_points or max(f["pc"].points.shape[1] for f in frames)
+        F = len(frames)
+        self.scans = torch.zeros(F, nmax, 3, device=device)
+        self.count = torch.zeros(F, dtype=torch.long, device=device)
+        c, s, r, first, prev = [], [], [], [], []
+        k = 0
+        for t in tracklets:
+            for j, f in enumerate(t):
+                pts = torch.as_tensor(f["pc"].points, dtype=torch.float32).t()[:nmax]
+                self.scans[k + j, : pts.shape[0]] = pts.to(device)
+                self.count[k + j] = pts.shape[0]
+                b = f["3d_bbox"]
+                c.append(torch.as_tensor(b.center, dtype=torch.float32))
+                s.append(torch.as_tensor(b.wlh, dtype=torch.float32))
+                r.append(torch.as_tensor(b.rotation_matrix, dtype=torch.float32))
+                first.append(k)
+                prev.append(k + max(j - 1, 0))
+            k += len(t)
+        self.center, self.wlh, self.rot = (torch.stack(x).to(device) for x in (c, s, r))
+        self.first = torch.tensor(first, device=device)
+        self.prev = torch.tensor(prev, device=device)
+        self.num_frames = F
+
+    def box(self, idx):
+        return bx.Box(self.center[idx], self.wlh[idx], self.rot[idx])
+
+    def valid(self, idx):
+        n = self.scans.shape[1]
+        return torch.arange(n, device=self.scans.device)[None, :] < self.count[idx][:, None]
+
+
+def transform_box(box: bx.Box, ref: bx.Box):
+    """points_utils.transform_box (:257-262): `box` expressed in the frame of `ref`."""
+    center = ((box.center - ref.center)[..., None, :] @ ref.rot)[..., 0, :]
+    return bx.Box(center, box.wlh, ref.rot.transpose(-1, -2) @ box.rot)
+
+
+def in_box_mask(points, box: bx.Box):
+    """points_utils.get_in_box_mask (:273-300): strictly inside the oriented box."""
+    local = bx.to_box_frame(points, box)
+    half = torch.stack([box.wlh[..., 1], box.wlh[..., 0], box.wlh[..., 2]], -1)[..., None, :] / 2     # l, w, h along x, y, z
+    return (local.abs() < half).all(-1)
+
+
+def siamese_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=None, generator=None):
+    """siamese_processing for the frames `frame_ids` (B,) with candidate indices `candidate_ids` (B,).
+    `draws` may carry explicit random numbers (tests): 'template_offset' (B, 3) uniform(-0.3, 0.3) draws, 'search_offset'
+    (B, 3) standard-normal draws, 'u_t', 'u_pick_t', 'u_s', 'u_pick_s' for the two resamplings.
+    Returns (batch dict, valid (B,) bool)."""
+    dev = data.scans.device
+    B = frame_ids.shape[0]
+    draws = draws or {}
+    deg = 5.0 if cfg.degrees else float(torch.deg2rad(torch.tensor(5.0)))
+    cand0 = candidate_ids == 0
+    # ---- template: offset the previous frame's box, merge with the first frame's crop (sampler.py:37-46)
+    off_t = draws.get("template_offset")
+    if off_t is None:
+        off_t = torch.rand(B, 3, device=dev, generator=generator) * 0.6 - 0.3
+    off_t = torch.where(cand0[:, None], torch.zeros_like(off_t), off_t * torch.tensor([1.0, 1.0, deg], device=dev))
+    i_first, i_prev = data.first[frame_ids], data.prev[frame_ids]
+    def limit_rand(key):
+        r = draws.get(key)
+        if r is None and cfg.data_limit_box:
+            r = torch.rand(B, 2, device=dev, generator=generator) * 2 - 1
+        return r
+    t_box = bx.offset_box(data.box(i_prev), off_t, degrees=cfg.degrees, limit_box=cfg.data_limit_box,
+                          rand=limit_rand("limit_rand_t"))
+    f_local, f_keep, _ = bx.crop_and_center(data.scans[i_first], data.box(i_first), offset=cfg.model_bb_offset, scale=cfg.model_bb_scale)
+    p_local, p_keep, canon = bx.crop_and_center(data.scans[i_prev], t_box, offset=cfg.model_bb_offset, scale=cfg.model_bb_scale)
+    cand = torch.cat([f_local, p_local], 1)
+    keep = torch.cat([f_keep & data.valid(i_first), p_keep & data.valid(i_prev)], 1)
+    template, _, n_t = resample_batched(cand, keep, cfg.template_size, draws.get("u_t"), draws.get("u_pick_t"), generator)
+    # ---- search area around the offset current box (sampler.py:50-63)
+    off_s = draws.get("search_offset")
+    if off_s is None:
+        off_s = torch.randn(B, 3, device=dev, generator=generator)
+    off_s = off_s * torch.tensor([1.0, 1.0, deg], device=dev).sqrt()            # N(0, diag(1, 1, 5 deg)): KalmanFiltering.reset
+    if cfg.get("num_candidates", 1) > 1:
+        off_s = torch.where(cand0[:, None], torch.zeros_like(off_s), off_s)
+    gt = data.box(frame_ids)
+    sample_bb = bx.offset_box(gt, off_s, degrees=cfg.degrees, limit_box=cfg.data_limit_box, rand=limit_rand("limit_rand_s"))
+    s_local, s_keep = bx.subwindow(data.scans[frame_ids], sample_bb, scale=cfg.search_bb_scale, offset=cfg.search_bb_offset)
+    s_keep = s_keep & data.valid(frame_ids)
+    s_box = transform_box(gt, sample_bb)
+    search, src, n_s = resample_batched(s_local, s_keep, cfg.search_size, draws.get("u_s"), draws.get("u_pick_s"), generator)
+    seg = in_box_mask(search, s_box).float()
+    box_label = torch.cat([s_box.center, -off_s[:, 2:3]], 1)
+    batch = {"template_points": template, "search_points": search, "box_label": box_label, "bbox_size": s_box.wlh,
+             "seg_label": seg}
+    if cfg.get("box_aware", False):
+        batch["points2cc_dist_t"] = bx.point_to_box_distance(template, canon)
+        batch["points2cc_dist_s"] = bx.point_to_box_distance(search, s_box)
+    batch["_n_template"], batch["_n_search"] = n_t, n_s          # survivor counts (diagnostics; dropped by next_batch)
+    return batch, (n_t > 20) & (n_s > 20)
+
+
+class DeviceSiameseSampler:
+    """Drop-in source of training batches: `next_batch()` returns the reference's batch dict, on the device."""
+
+    def __init__(self, tracklets, cfg, device, oversample=1.25, seed=0, max_points=None):
+        self.data = tracklets if isinstance(tracklets, DeviceTracklets) else DeviceTracklets(tracklets, device, max_points)
+        self.cfg = cfg
+        self.gen = torch.Generator(device=device).manual_seed(seed)
+        self.oversample = oversample
+        self.num_candidates = cfg.get("num_candidates", 1)
+
+    def next_batch(self, batch_size=None):
+        B = batch_size or self.cfg.batch_size
+        pool = int(B * self.oversample) + 1
+        dev = self.data.scans.device
+        index = torch.randint(0, self.data.num_frames * self.num_candidates, (pool,), device=dev, generator=self.gen)
+        batch, valid = siamese_batch(self.data, self.cfg, index // self.num_candidates, index % self.num_candidates,
+                                     generator=self.gen)
+        order = torch.argsort((~valid).to(torch.int8), stable=True)[:B]       # valid samples first, original order kept
+        return {k: v[order] for k, v in batch.items() if not k.startswith("_")}, valid[order]

@@ -31,3 +31,20 @@ def resample(points, keep, size, generator=None, indices=None, u_perm=None, u_pi
     src = torch.where(n >= size, order[:size], order[pick])
     out = points[src]
     return torch.where(n > 2, out, torch.zeros_like(out)), src
+
+
+def resample_batched(points, keep, size, u_perm=None, u_pick=None, generator=None):
+    """Batched form of `resample`: points (B, N, 3), keep (B, N) -> (B, size, 3) points, (B, size) source indices and the
+    per-sample survivor count (B,)."""
+    B, n_all = keep.shape
+    dev = points.device
+    n = keep.sum(1)
+    u = torch.rand(B, n_all, device=dev, generator=generator) if u_perm is None else u_perm
+    order = torch.argsort(torch.where(keep, u, torch.full_like(u, 2.0)), dim=1)
+    if n_all < size:
+        order = torch.cat([order, order.new_zeros(B, size - n_all)], 1)
+    up = torch.rand(B, size, device=dev, generator=generator) if u_pick is None else u_pick
+    pick = torch.minimum((up * n[:, None]).long(), torch.clamp(n - 1, min=0)[:, None])
+    src = torch.where((n >= size)[:, None], order[:, :size], torch.gather(order, 1, pick))
+    out = torch.gather(points, 1, src[..., None].expand(-1, -1, points.shape[-1]))
+    return torch.where((n > 2)[:, None, None], out, torch.zeros_like(out)), src, n

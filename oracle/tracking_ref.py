@@ -59,8 +59,12 @@ def regularize_pc(points, sample_size, seed=None):
     return np.zeros((sample_size, 3), dtype="float32"), None
 
 
-def get_offset_bb(box, offset, degrees=True, use_z=False, limit_box=True, rng=np.random):
-    """points_utils.py:43-85.  Net effect: centre += R @ (dx, dy, dz*use_z), R <- R @ rotz(angle)."""
+def get_offset_bb(box, offset, degrees=True, use_z=False, limit_box=True, rand=None):
+    """points_utils.py:43-85.  Net effect: centre += R @ (dx, dy, dz*use_z), R <- R @ rotz(angle).
+    `rand` = (r_dx, r_dy): the uniform(-1, 1) numbers limit_box substitutes for out-of-range dx / dy (the reference draws
+    them from numpy's global RNG; drawn here the same way when not given)."""
+    if rand is None:
+        rand = (np.random.uniform(-1, 1), np.random.uniform(-1, 1))
     offset = np.array(offset, dtype=np.float64)
     new_box = copy.deepcopy(box)
     rot, trans = box.rot.copy(), box.center.copy()
@@ -72,9 +76,9 @@ def get_offset_bb(box, offset, degrees=True, use_z=False, limit_box=True, rng=np
     new_box.rotate(rotz(ang, degrees))
     if limit_box:
         if offset[0] > new_box.wlh[0]:
-            offset[0] = rng.uniform(-1, 1)
+            offset[0] = rand[0]
         if offset[1] > min(new_box.wlh[1], 2):
-            offset[1] = rng.uniform(-1, 1)
+            offset[1] = rand[1]
         if use_z and offset[2] > new_box.wlh[2]:
             offset[2] = 0
     new_box.translate(np.array([offset[0], offset[1], offset[2] if use_z else 0.0]))
@@ -225,3 +229,64 @@ def precision(accs, n=21, max_accuracy=2.0):
         return 0.0
     ys = np.array([(a <= t).mean() for t in xs])
     return float(np.trapezoid(ys, xs) * 100 / max_accuracy)
+
+
+# ---- training batch construction (datasets/sampler.py) -------------------------------------------------------------
+def transform_box(box, ref):
+    """points_utils.py:257-262."""
+    b = copy.deepcopy(box)
+    b.translate(-ref.center)
+    b.rotate(ref.rot.T)
+    return b
+
+
+def get_in_box_mask(points, box):
+    """points_utils.py:273-300 on a (3, N) array."""
+    tmp = copy.deepcopy(box)
+    rot_t, trans = box.rot.T.copy(), -box.center
+    pts = rot_t @ (points + trans[:, None])
+    tmp.translate(trans)
+    tmp.rotate(rot_t)
+    c = tmp.corners()
+    maxi, mini = c.max(1), c.min(1)
+    keep = np.ones(points.shape[1], dtype=bool)
+    for a in range(3):
+        keep &= (pts[a] > mini[a]) & (pts[a] < maxi[a])
+    return keep
+
+
+def siamese_processing(first, template, search, candidate_id, cfg, template_offset, search_offset, idx_t=None, idx_s=None,
+                       limit_rand_t=None, limit_rand_s=None):
+    """datasets/sampler.py:16-79 with the random draws passed in: `template_offset` = the uniform(-0.3, 0.3) triple,
+    `search_offset` = the KalmanFiltering sample; `idx_t` / `idx_s` = regularize_pc's index draws.
+    Frames are (points (3, N), Box).  Returns the data dict plus the survivor counts."""
+    (first_pc, first_box), (t_pc, t_box), (s_pc, s_box) = first, template, search
+    deg = 5 if cfg["degrees"] else np.deg2rad(5)
+    if candidate_id == 0:
+        off_t = np.zeros(3)
+    else:
+        off_t = np.array(template_offset, dtype=np.float64)
+        off_t[2] = off_t[2] * deg
+    t_box = get_offset_bb(t_box, off_t, limit_box=cfg["data_limit_box"], degrees=cfg["degrees"], rand=limit_rand_t)
+    model_pc, model_box = get_model([first_pc, t_pc], [first_box, t_box], scale=cfg["model_bb_scale"], offset=cfg["model_bb_offset"])
+    if candidate_id == 0 and cfg.get("num_candidates", 1) > 1:
+        off_s = np.zeros(3)
+    else:
+        off_s = np.array(search_offset, dtype=np.float64)
+    sample_bb = get_offset_bb(s_box, off_s, limit_box=cfg["data_limit_box"], degrees=cfg["degrees"], rand=limit_rand_s)
+    crop = generate_subwindow(s_pc, sample_bb, scale=cfg["search_bb_scale"], offset=cfg["search_bb_offset"])
+    s_box = transform_box(s_box, sample_bb)
+    seg = get_in_box_mask(crop, s_box).astype(int)
+    reg = [s_box.center[0], s_box.center[1], s_box.center[2], -off_s[2]]
+    tp = model_pc.T[idx_t] if idx_t is not None else regularize_pc(model_pc.T, cfg["template_size"])[0]
+    if idx_s is None:
+        sp, idx_s = regularize_pc(crop.T, cfg["search_size"])
+    else:
+        sp = crop.T[idx_s]
+    out = {"template_points": tp.astype("float32"), "search_points": sp.astype("float32"), "box_label": np.array(reg, dtype="float32"),
+           "bbox_size": s_box.wlh, "seg_label": seg[idx_s].astype("float32"), "n_template": model_pc.shape[1], "n_search": crop.shape[1],
+           "_model_pc": model_pc, "_model_box": model_box, "_crop": crop, "_seg": seg, "_search_box": s_box}
+    if cfg.get("box_aware", False):
+        out["points2cc_dist_t"] = get_point_to_box_distance(tp, model_box).astype("float32")
+        out["points2cc_dist_s"] = get_point_to_box_distance(sp, s_box).astype("float32")
+    return out

@@ -1,0 +1,77 @@
+"""On-device construction of siamese training batches against the numpy restatement of
+datasets/sampler.py:16-79 (oracle/tracking_ref.py; parity unpinned, see its header), with the random draws shared."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tracking_ref as R
+from open3dsot_b200.config import load_config
+from open3dsot_b200.datasets.device_sampler import DeviceSiameseSampler, DeviceTracklets, siamese_batch
+from open3dsot_b200.datasets.synthetic import synthetic_sequence
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rows_in(rows, pool, tol=2e-5):
+    """every row of `rows` (k, 3) occurs in `pool` (n, 3)"""
+    d = np.abs(rows[:, None, :] - pool[None, :, :]).max(-1)
+    return d.min(1).max() < tol, d.argmin(1)
+
+
+@pytest.mark.parametrize("cfg_name", ["BAT_Car.yaml", "P2B_Car.yaml"])
+def test_batch_matches_reference_restatement(cfg_name):
+    cfg = load_config(os.path.join(ROOT, "cfgs", cfg_name), {})
+    tracklets = [synthetic_sequence(n_frames=4, n_points=3000, seed=21 + i, n_object=400) for i in range(2)]
+    data = DeviceTracklets(tracklets, "cpu")
+    frames = [f for t in tracklets for f in t]
+    B = 8
+    g = torch.Generator().manual_seed(5)
+    frame_ids = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7])
+    cand = torch.tensor([0, 1, 2, 3, 0, 1, 2, 3])
+    draws = {"template_offset": torch.rand(B, 3, generator=g) * 0.6 - 0.3, "search_offset": torch.randn(B, 3, generator=g) * 0.6,
+             "limit_rand_t": torch.rand(B, 2, generator=g) * 2 - 1, "limit_rand_s": torch.rand(B, 2, generator=g) * 2 - 1}
+    batch, valid = siamese_batch(data, cfg, frame_ids, cand, draws=draws, generator=g)
+    assert bool(valid.all())
+    deg = 5.0 if cfg.degrees else np.deg2rad(5.0)
+    def fr(f):
+        bb = f["3d_bbox"]
+        return f["pc"].points.astype(np.float64), R.Box(bb.center, bb.wlh, bb.rotation_matrix)
+
+    for b in range(B):
+        k = int(frame_ids[b])
+        first, prev = frames[int(data.first[k])], frames[int(data.prev[k])]
+        off_s = draws["search_offset"][b].double().numpy() * np.sqrt([1.0, 1.0, deg])     # N(0, diag(1, 1, 5 deg))
+        want = R.siamese_processing(fr(first), fr(prev), fr(frames[k]), int(cand[b]), cfg,
+                                    draws["template_offset"][b].double().numpy(), off_s,
+                                    limit_rand_t=draws["limit_rand_t"][b].tolist(), limit_rand_s=draws["limit_rand_s"][b].tolist())
+        assert int(batch["_n_template"][b]) == want["n_template"] and int(batch["_n_search"][b]) == want["n_search"]
+        assert np.abs(batch["box_label"][b].numpy() - want["box_label"]).max() < 1e-4
+        assert np.abs(batch["bbox_size"][b].numpy() - want["bbox_size"]).max() < 1e-6
+        # the resampled clouds are subsets of the reference's crops (a different random subset), with the reference's labels
+        ok, _ = _rows_in(batch["template_points"][b].numpy(), want["_model_pc"].T)
+        assert ok
+        ok, where = _rows_in(batch["search_points"][b].numpy(), want["_crop"].T)
+        assert ok
+        assert np.array_equal(batch["seg_label"][b].numpy() > 0.5, want["_seg"][where].astype(bool))
+        assert 0 < batch["seg_label"][b].sum() < cfg.search_size                # object and background both present
+        if cfg.get("box_aware", False):
+            tp, sp = batch["template_points"][b].double().numpy(), batch["search_points"][b].double().numpy()
+            assert np.abs(batch["points2cc_dist_t"][b].numpy() - R.get_point_to_box_distance(tp, want["_model_box"])).max() < 1e-4
+            assert np.abs(batch["points2cc_dist_s"][b].numpy() - R.get_point_to_box_distance(sp, want["_search_box"])).max() < 1e-4
+
+
+def test_sampler_returns_reference_batch_schema():
+    cfg = load_config(os.path.join(ROOT, "cfgs", "BAT_Car.yaml"), {"batch_size": 6})
+    tracklets = [synthetic_sequence(n_frames=5, n_points=3000, seed=3 + i, n_object=400) for i in range(3)]
+    smp = DeviceSiameseSampler(tracklets, cfg, "cpu", seed=1)
+    batch, valid = smp.next_batch()
+    assert bool(valid.all())
+    want = {"template_points": (6, cfg.template_size, 3), "search_points": (6, cfg.search_size, 3), "box_label": (6, 4),
+            "bbox_size": (6, 3), "seg_label": (6, cfg.search_size), "points2cc_dist_t": (6, cfg.template_size, 9),
+            "points2cc_dist_s": (6, cfg.search_size, 9)}
+    assert {k: tuple(v.shape) for k, v in batch.items()} == want
+    assert all(v.dtype == torch.float32 for v in batch.values())
+    b2, _ = smp.next_batch()
+    assert not torch.equal(b2["search_points"], batch["search_points"])      # a new draw every call

@@ -59,10 +59,7 @@ def test_limit_box_replaces_out_of_range_offsets():
     rand = torch.tensor([0.25, -0.5], dtype=torch.float64)
     got = bx.offset_box(tb, big, True, True, True, rand=rand)
 
-    class Fixed:                                         # the reference draws uniform(-1, 1) from the global numpy RNG
-        def uniform(self, a, b):
-            return 0.25
-    want = R.get_offset_bb(ob, big.tolist(), degrees=True, use_z=True, limit_box=True, rng=Fixed())
+    want = R.get_offset_bb(ob, big.tolist(), degrees=True, use_z=True, limit_box=True, rand=(0.25, -0.5))
     assert np.abs(got.center.numpy() - want.center).max() < 1e-12
 
 
