@@ -137,3 +137,28 @@ class DeviceSiameseSampler:
                                      generator=self.gen)
         order = torch.argsort((~valid).to(torch.int8), stable=True)[:B]       # valid samples first, original order kept
         return {k: v[order] for k, v in batch.items() if not k.startswith("_")}, valid[order]
+
+
+class PrefetchingSampler:
+    """Builds batch i+1 on a side stream while the consumer's stream works on batch i (the construction is a few hundred
+    small launches that fit into the gaps of the training step's persistent kernels)."""
+
+    def __init__(self, sampler: DeviceSiameseSampler, batch_size=None):
+        self.sampler, self.batch_size = sampler, batch_size
+        self.stream = torch.cuda.Stream()
+        self._next = None
+        self._launch()
+
+    def _launch(self):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self._next = self.sampler.next_batch(self.batch_size)
+
+    def next_batch(self):
+        main = torch.cuda.current_stream()
+        main.wait_stream(self.stream)
+        batch, valid = self._next
+        for t in list(batch.values()) + [valid]:
+            t.record_stream(main)                       # allocated on the side stream, consumed on the caller's
+        self._launch()
+        return batch, valid
