@@ -251,7 +251,7 @@ def sampler_cpu_baseline(cfg, tracklets, n_pairs=24):
 def run_sampler(args):
     """Secondary mode: training batches built on the device, alone and feeding the training step."""
     from open3dsot_b200.config import load_config
-    from open3dsot_b200.datasets.device_sampler import DeviceSiameseSampler, PrefetchingSampler
+    from open3dsot_b200.datasets.device_sampler import DeviceSiameseSampler
     from open3dsot_b200.datasets.synthetic import synthetic_sequence
     from open3dsot_b200.engine import TrainStep
     from open3dsot_b200.models import get_model
@@ -274,15 +274,14 @@ def run_sampler(args):
     torch.manual_seed(0)
     net = get_model(cfg.net_model)(cfg).to(dev).train()
     eng = TrainStep(net, lr=cfg.lr, weight_decay=cfg.wd, use_graph=True, warmup=2)
-    pre = PrefetchingSampler(smp)                      # batch i+1 is built on a side stream during step i
     for _ in range(w + 3):
-        eng.step(pre.next_batch()[0])
+        eng.step(smp.next_batch()[0])
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
     e0.record()
     for _ in range(n):
-        loss = eng.step(pre.next_batch()[0])
+        loss = eng.step(smp.next_batch()[0])
     e1.record()
     torch.cuda.synchronize()
     ms_step = e0.elapsed_time(e1) / n

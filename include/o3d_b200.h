@@ -245,6 +245,14 @@ int o3d_pw_wgrad_tc2(const float* g, int ldg, const float* y, int ldy, const flo
 int o3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float* state,
                   float beta1, float beta2, float eps, float weight_decay, void* stream);
 
+/* Block 5 — box-frame crop of LiDAR scans (tracking frame loop and training-pair construction; replaces the host numpy of
+ * datasets/points_utils.py generate_subwindow :223-254, cropAndCenterPC :102-124, crop_pc_axis_aligned :147-173).
+ *   local[b,i,:] = R[b]^T (scans[frame[b],i,:] - center[b]);  keep[b,i] = i < count[frame[b]] && |local| < half[b] per axis
+ * scans [F,N,3]; count [F] int64 or NULL (all N valid); frame [B] int64 or NULL (frame b = b); rot [B,9] row-major with
+ * the box axes in its columns; half [B,3] = (l, w, h) * scale / 2 + offset.                                        */
+int o3d_crop_box_frame(const float* scans, const long long* count, const long long* frame, const float* center,
+                       const float* rot, const float* half, int B, int N, float* local, unsigned char* keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "o3d_pw_wgrad_tc2": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p,
                          ctypes.c_longlong, _p],
     "o3d_adam_step": [_p, _p, _p, _p, ctypes.c_longlong, _p, _f, _f, _f, _f, _p],
+    "o3d_crop_box_frame": [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p],
     "o3d_stack_workspace_bytes": [_p, _i],
     "o3d_stack_forward": [_p, _p, _p, _p, _i, _p],
     "o3d_stack_backward": [_p, _p, _p, _p, _p, _p, _p, _p],

@@ -74,13 +74,14 @@ def siamese_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=No
     dev = data.scans.device
     B = frame_ids.shape[0]
     draws = draws or {}
-    deg = 5.0 if cfg.degrees else float(torch.deg2rad(torch.tensor(5.0)))
+    deg = 5.0 if cfg.degrees else 0.08726646259971647                 # 5 degrees, in the unit the boxes are offset in
+    ang_scale = torch.cat([torch.ones(2, device=dev), torch.full((1,), deg, device=dev)])   # fills only: graph-capturable
     cand0 = candidate_ids == 0
     # ---- template: offset the previous frame's box, merge with the first frame's crop (sampler.py:37-46)
     off_t = draws.get("template_offset")
     if off_t is None:
         off_t = torch.rand(B, 3, device=dev, generator=generator) * 0.6 - 0.3
-    off_t = torch.where(cand0[:, None], torch.zeros_like(off_t), off_t * torch.tensor([1.0, 1.0, deg], device=dev))
+    off_t = torch.where(cand0[:, None], torch.zeros_like(off_t), off_t * ang_scale)
     i_first, i_prev = data.first[frame_ids], data.prev[frame_ids]
     def limit_rand(key):
         r = draws.get(key)
@@ -89,22 +90,22 @@ def siamese_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=No
         return r
     t_box = bx.offset_box(data.box(i_prev), off_t, degrees=cfg.degrees, limit_box=cfg.data_limit_box,
                           rand=limit_rand("limit_rand_t"))
-    f_local, f_keep, _ = bx.crop_and_center(data.scans[i_first], data.box(i_first), offset=cfg.model_bb_offset, scale=cfg.model_bb_scale)
-    p_local, p_keep, canon = bx.crop_and_center(data.scans[i_prev], t_box, offset=cfg.model_bb_offset, scale=cfg.model_bb_scale)
+    f_local, f_keep = bx.crop_in_box_frame(data.scans, data.box(i_first), cfg.model_bb_scale, cfg.model_bb_offset, i_first, data.count)
+    p_local, p_keep = bx.crop_in_box_frame(data.scans, t_box, cfg.model_bb_scale, cfg.model_bb_offset, i_prev, data.count)
+    canon = bx.Box(torch.zeros_like(t_box.center), t_box.wlh, torch.eye(3, device=dev).expand_as(t_box.rot))
     cand = torch.cat([f_local, p_local], 1)
-    keep = torch.cat([f_keep & data.valid(i_first), p_keep & data.valid(i_prev)], 1)
+    keep = torch.cat([f_keep, p_keep], 1)
     template, _, n_t = resample_batched(cand, keep, cfg.template_size, draws.get("u_t"), draws.get("u_pick_t"), generator)
     # ---- search area around the offset current box (sampler.py:50-63)
     off_s = draws.get("search_offset")
     if off_s is None:
         off_s = torch.randn(B, 3, device=dev, generator=generator)
-    off_s = off_s * torch.tensor([1.0, 1.0, deg], device=dev).sqrt()            # N(0, diag(1, 1, 5 deg)): KalmanFiltering.reset
+    off_s = off_s * ang_scale.sqrt()            # N(0, diag(1, 1, 5 deg)): KalmanFiltering.reset
     if cfg.get("num_candidates", 1) > 1:
         off_s = torch.where(cand0[:, None], torch.zeros_like(off_s), off_s)
     gt = data.box(frame_ids)
     sample_bb = bx.offset_box(gt, off_s, degrees=cfg.degrees, limit_box=cfg.data_limit_box, rand=limit_rand("limit_rand_s"))
-    s_local, s_keep = bx.subwindow(data.scans[frame_ids], sample_bb, scale=cfg.search_bb_scale, offset=cfg.search_bb_offset)
-    s_keep = s_keep & data.valid(frame_ids)
+    s_local, s_keep = bx.crop_in_box_frame(data.scans, sample_bb, cfg.search_bb_scale, cfg.search_bb_offset, frame_ids, data.count)
     s_box = transform_box(gt, sample_bb)
     search, src, n_s = resample_batched(s_local, s_keep, cfg.search_size, draws.get("u_s"), draws.get("u_pick_s"), generator)
     seg = in_box_mask(search, s_box).float()
@@ -119,17 +120,25 @@ def siamese_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=No
 
 
 class DeviceSiameseSampler:
-    """Drop-in source of training batches: `next_batch()` returns the reference's batch dict, on the device."""
+    """Drop-in source of training batches: `next_batch()` returns the reference's batch dict, on the device.
+    On CUDA the construction (≈ 340 small launches, host-bound when issued eagerly) is captured once in a CUDA graph;
+    every replay draws new frames and offsets (graph-safe philox offsets of the default CUDA generator) into the same
+    static output tensors — consume or copy a batch before asking for the next one."""
 
-    def __init__(self, tracklets, cfg, device, oversample=1.25, seed=0, max_points=None):
+    def __init__(self, tracklets, cfg, device, oversample=1.25, seed=0, max_points=None, use_graph=True):
         self.data = tracklets if isinstance(tracklets, DeviceTracklets) else DeviceTracklets(tracklets, device, max_points)
         self.cfg = cfg
-        self.gen = torch.Generator(device=device).manual_seed(seed)
+        dev = self.data.scans.device
+        self.use_graph = bool(use_graph) and dev.type == "cuda"
+        # a captured graph can only advance the default CUDA generator; the eager path keeps its own seeded generator
+        self.gen = None if self.use_graph else torch.Generator(device=dev).manual_seed(seed)
+        if self.use_graph:
+            torch.cuda.manual_seed(seed)
         self.oversample = oversample
         self.num_candidates = cfg.get("num_candidates", 1)
+        self._graphs = {}
 
-    def next_batch(self, batch_size=None):
-        B = batch_size or self.cfg.batch_size
+    def _build(self, B):
         pool = int(B * self.oversample) + 1
         dev = self.data.scans.device
         index = torch.randint(0, self.data.num_frames * self.num_candidates, (pool,), device=dev, generator=self.gen)
@@ -138,27 +147,20 @@ class DeviceSiameseSampler:
         order = torch.argsort((~valid).to(torch.int8), stable=True)[:B]       # valid samples first, original order kept
         return {k: v[order] for k, v in batch.items() if not k.startswith("_")}, valid[order]
 
-
-class PrefetchingSampler:
-    """Builds batch i+1 on a side stream while the consumer's stream works on batch i (the construction is a few hundred
-    small launches that fit into the gaps of the training step's persistent kernels)."""
-
-    def __init__(self, sampler: DeviceSiameseSampler, batch_size=None):
-        self.sampler, self.batch_size = sampler, batch_size
-        self.stream = torch.cuda.Stream()
-        self._next = None
-        self._launch()
-
-    def _launch(self):
-        self.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
-            self._next = self.sampler.next_batch(self.batch_size)
-
-    def next_batch(self):
-        main = torch.cuda.current_stream()
-        main.wait_stream(self.stream)
-        batch, valid = self._next
-        for t in list(batch.values()) + [valid]:
-            t.record_stream(main)                       # allocated on the side stream, consumed on the caller's
-        self._launch()
-        return batch, valid
+    def next_batch(self, batch_size=None):
+        B = batch_size or self.cfg.batch_size
+        if not self.use_graph:
+            return self._build(B)
+        if B not in self._graphs:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._build(B)                                   # warm-up: allocator, lazy initialisations
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._build(B)
+            self._graphs[B] = (g, out)
+        g, out = self._graphs[B]
+        g.replay()
+        return out

@@ -174,3 +174,19 @@ def three_nn_interpolate_grad(grad_out_cl, idx, weight, m):
     _call("o3d_three_nn_interpolate_grad", grad_out_cl.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, n, int(m), c,
           g.data_ptr(), _stream())
     return g
+
+
+# ------------------------------------------------------------------ box-frame crop (tracking loop / training sampler)
+def crop_box_frame(scans, center, rot, half, frame=None, count=None):
+    """scans (F, N, 3) fp32 CUDA; center (B, 3), rot (B, 3, 3), half (B, 3); frame (B,) int64 picks a scan per sample
+    (None: sample b reads scan b), count (F,) int64 = valid points per scan.  Returns local (B, N, 3), keep (B, N) bool."""
+    _chk_f(scans, "scans")
+    F, N, _ = scans.shape
+    B = center.shape[0]
+    center, rot, half = (t.contiguous().float() for t in (center, rot, half))
+    local = torch.empty(B, N, 3, device=scans.device)
+    keep = torch.empty(B, N, dtype=torch.bool, device=scans.device)
+    _call("o3d_crop_box_frame", scans.data_ptr(), None if count is None else count.data_ptr(),
+          None if frame is None else frame.data_ptr(), center.data_ptr(), rot.data_ptr(), half.data_ptr(), B, N,
+          local.data_ptr(), keep.data_ptr(), _stream())
+    return local, keep

@@ -88,6 +88,25 @@ def crop_and_center(points, box: Box, offset=0.0, scale=1.0):
     return local, coarse & axis_aligned_mask(local, canon, offset=offset, scale=scale), canon
 
 
+def crop_in_box_frame(scans, box: Box, scale, offset, frame=None, count=None):
+    """The common core of generate_subwindow (:223-254) and cropAndCenterPC (:102-124) over a batch: scans (F, N, 3), one box
+    per sample (B leading dim), `frame` (B,) picks each sample's scan, `count` (F,) the valid points per scan.
+    Returns (local (B, N, 3) = points in the box frame, keep (B, N) = strictly inside the scaled box padded by `offset`).
+    cropAndCenterPC's coarse world-frame pre-crop (4x scale, 2x offset) contains the exact box and is skipped.
+    CUDA fp32 inputs go through one fused kernel (csrc/geometry.cu); other tensors through the tensor formulation."""
+    half = torch.stack([box.wlh[..., 1], box.wlh[..., 0], box.wlh[..., 2]], -1) * (scale / 2) + offset      # l, w, h on x, y, z
+    if scans.is_cuda and scans.dtype == torch.float32:
+        from .. import ops
+        return ops.crop_box_frame(scans.contiguous(), box.center, box.rot, half, frame, count)
+    pts = scans if frame is None else scans[frame]
+    local = to_box_frame(pts, box)
+    keep = (local.abs() < half[..., None, :]).all(-1)
+    if count is not None:
+        n = count if frame is None else count[frame]
+        keep = keep & (torch.arange(pts.shape[-2], device=pts.device)[None, :] < n[:, None])
+    return local, keep
+
+
 def point_to_box_distance(points, box: Box, wlh_factor=1.0):
     """get_point_to_box_distance (:127-144): (..., N, 9) distances to the centre and the eight corners."""
     ref = torch.cat([box.center[..., None, :], corners(box, wlh_factor)], -2)                  # (..., 9, 3)

@@ -70,12 +70,14 @@ class DeviceTracker:
     def _inputs(self):
         cfg, box = self.cfg, self._box()
         # search area: current scan in the frame of the reference box (= previous result)
-        s_local, s_keep = bx.subwindow(self.scan, box, scale=cfg.search_bb_scale, offset=cfg.search_bb_offset)
+        b1 = bx.Box(box.center[None], box.wlh[None], box.rot[None])
+        s_local, s_keep = bx.crop_in_box_frame(self.scan[None], b1, cfg.search_bb_scale, cfg.search_bb_offset)
+        s_local, s_keep = s_local[0], s_keep[0]
         search, _ = resample(s_local, s_keep & self.scan_valid, cfg.search_size, u_perm=self.u_s[0], u_pick=self.u_s[1])
         # template: first-frame crop (+ previous-frame crop around the previous result)
         mode = cfg.shape_aggregation.upper()
-        p_local, p_keep, _ = bx.crop_and_center(self.prev_scan, box, offset=cfg.model_bb_offset, scale=cfg.model_bb_scale)
-        p_keep = p_keep & self.prev_valid
+        p_local, p_keep = bx.crop_in_box_frame(self.prev_scan[None], b1, cfg.model_bb_scale, cfg.model_bb_offset)
+        p_local, p_keep = p_local[0], p_keep[0] & self.prev_valid
         if "FIRSTANDPREVIOUS" in mode:
             cand, keep = torch.cat([self.first_local, p_local]), torch.cat([self.first_keep, p_keep])
         elif "FIRST" in mode:

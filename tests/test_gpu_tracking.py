@@ -61,3 +61,27 @@ def test_graph_replay_equals_eager_frames():
         tracks.append([trk.step(p).center.clone() for p in pts[1:]])
     for a, b in zip(*tracks):
         assert float((a - b).abs().max()) < 1e-3
+
+
+def test_crop_kernel_matches_tensor_formulation():
+    """csrc/geometry.cu against boxes.crop_in_box_frame's tensor path (the one the CPU tests pin to the numpy restatement)."""
+    from open3dsot_b200.tracking import boxes as bx
+    g = torch.Generator().manual_seed(0)
+    F, N, B = 5, 4099, 7
+    scans = torch.randn(F, N, 3, generator=g) * 4
+    count = torch.tensor([N, 4000, 17, 0, 2500])
+    frame = torch.tensor([0, 1, 2, 3, 4, 1, 0])
+    q, _ = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+    q = q * torch.sign(torch.linalg.det(q))[:, None, None]
+    box = bx.Box(torch.randn(B, 3, generator=g), torch.rand(B, 3, generator=g) * 3 + 1, q)
+    want_l, want_k = bx.crop_in_box_frame(scans, box, 1.25, 2.0, frame, count)                   # CPU tensors: tensor path
+    cu = bx.Box(*(t.cuda() for t in box))
+    got_l, got_k = bx.crop_in_box_frame(scans.cuda(), cu, 1.25, 2.0, frame.cuda(), count.cuda())  # CUDA: fused kernel
+    assert float((got_l.cpu() - want_l).abs().max()) < 1e-5
+    half = torch.stack([box.wlh[:, 1], box.wlh[:, 0], box.wlh[:, 2]], -1) * 0.625 + 2.0
+    edge = ((want_l.abs() - half[:, None, :]).abs() < 1e-4).any(-1)                               # rounding may flip these
+    assert bool(((got_k.cpu() == want_k) | edge).all())
+    assert int(got_k.cpu()[2].sum()) <= 17 and int(got_k.cpu()[3].sum()) == 0                    # padding rows never kept
+    l1, k1 = bx.crop_in_box_frame(scans[:B].cuda() if F >= B else scans.cuda().repeat(2, 1, 1)[:B], cu, 1.0, 0.0)   # frame=None, count=None
+    ref_l, ref_k = bx.crop_in_box_frame((scans.repeat(2, 1, 1))[:B], box, 1.0, 0.0)
+    assert float((l1.cpu() - ref_l).abs().max()) < 1e-5
