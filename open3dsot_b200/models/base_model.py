@@ -168,10 +168,44 @@ class MatchingBaseModel(BaseModel):
         return self.prepare_input(template_pc, search_pc_crop, canonical_box), ref_bb
 
 
+def motion_input(prev_local, prev_keep, this_local, this_keep, wlh, size, first_frame, box_aware, draw=None):
+    """MotionBaseModel.build_input_dict (:255-303) from the two sub-window crops (points in the reference box's frame +
+    keep masks): resample both to `size`, append the timestamp (0 / 0.1) and prior-targetness (in the 1.25x box: 1 / 0 on
+    the first tracked frame, 0.8 / 0.2 afterwards; 0.5 for the current frame) channels, stack previous over current, and
+    give the BoxCloud of the previous half (zeros for the current half).  `draw(points, keep, size)` does the resampling."""
+    dev = prev_local.device
+    prev_pts = draw(prev_local, prev_keep, size)
+    this_pts = draw(this_local, this_keep, size)
+    canon = bx.Box(torch.zeros(3, device=dev), wlh, torch.eye(3, device=dev))
+    half = torch.stack([wlh[1], wlh[0], wlh[2]]) * (1.25 / 2)
+    inside = (prev_pts.abs() <= half).all(-1).float()          # nuscenes points_in_box: inclusive bounds
+    mask_prev = inside if first_frame else inside * 0.6 + 0.2
+    cols = lambda pts, t, m: torch.cat([pts, torch.full_like(pts[:, :1], t), m[:, None]], -1)
+    stack = torch.cat([cols(prev_pts, 0.0, mask_prev), cols(this_pts, 0.1, torch.full_like(mask_prev, 0.5))], 0)
+    data = {"points": stack[None]}
+    if box_aware:
+        bc = bx.point_to_box_distance(prev_pts, canon)
+        data["candidate_bc"] = torch.cat([bc, torch.zeros_like(bc)], 0)[None]
+    return data
+
+
 class MotionBaseModel(BaseModel):
-    """Base of the motion-centric models (models/base_model.py:250-303); the input-dict construction for tracking
-    evaluation (:255-303) needs the dataset stack and is out of scope."""
+    """Base of the motion-centric models (models/base_model.py:250-303)."""
 
     def __init__(self, config, **kwargs):
         super().__init__(config, **kwargs)
         self.save_hyperparameters()
+
+    def build_input_dict(self, sequence, frame_id, results_bbs, **kwargs):
+        assert frame_id > 0, "no need to construct an input_dict at frame 0"
+        cfg = self.config
+        ref = _tbox(results_bbs[-1], self.device)
+        crops = []
+        for f in (sequence[frame_id - 1], sequence[frame_id]):
+            local, keep = bx.subwindow(_points(f['pc'], self.device), ref, scale=cfg.bb_scale, offset=cfg.bb_offset)
+            crops += [local, keep]
+
+        def draw(points, keep, size):
+            return regularize(points[keep], size, seed=1)[0]
+        data = motion_input(*crops, ref.wlh, cfg.point_sample_size, frame_id == 1, getattr(cfg, 'box_aware', False), draw)
+        return data, results_bbs[-1]

@@ -290,3 +290,28 @@ def siamese_processing(first, template, search, candidate_id, cfg, template_offs
         out["points2cc_dist_t"] = get_point_to_box_distance(tp, model_box).astype("float32")
         out["points2cc_dist_s"] = get_point_to_box_distance(sp, s_box).astype("float32")
     return out
+
+
+def motion_build_input(prev_pts, this_pts, ref_box, cfg, frame_id):
+    """models/base_model.py:255-303 (MotionBaseModel.build_input_dict) on (3, N) scans; regularize_pc with seed=1.
+    nuscenes' points_in_box(box, pts, 1.25) is restated as the inclusive test in the box frame (its three projections
+    0 <= v.e <= e.e are exactly -half <= local <= half)."""
+    n = cfg["point_sample_size"]
+    prev_crop = generate_subwindow(prev_pts, ref_box, cfg["bb_scale"], cfg["bb_offset"])
+    this_crop = generate_subwindow(this_pts, ref_box, cfg["bb_scale"], cfg["bb_offset"])
+    canon = transform_box(ref_box, ref_box)
+    pp, _ = regularize_pc(prev_crop.T, n, seed=1)
+    tp, _ = regularize_pc(this_crop.T, n, seed=1)
+    half = np.array([canon.wlh[1], canon.wlh[0], canon.wlh[2]]) * 1.25 / 2
+    mask_prev = (np.abs(pp) <= half).all(1).astype(float)
+    if frame_id != 1:
+        mask_prev = np.where(mask_prev == 0, 0.2, 0.8)
+    mask_this = np.full(mask_prev.shape, 0.5)
+    prev = np.concatenate([pp, np.full((n, 1), 0.0), mask_prev[:, None]], -1)
+    this = np.concatenate([tp, np.full((n, 1), 0.1), mask_this[:, None]], -1)
+    stack = np.concatenate([prev, this], 0)
+    out = {"points": stack[None].astype("float32")}
+    if cfg.get("box_aware", False):
+        bc = get_point_to_box_distance(stack[:n, :3], canon)
+        out["candidate_bc"] = np.concatenate([bc, np.zeros_like(bc)], 0)[None].astype("float32")
+    return out

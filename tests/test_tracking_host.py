@@ -179,3 +179,26 @@ def test_device_tracker_matches_the_host_loop_on_cpu():
         # different random subsets of the same crops -> the stand-in's centroid estimate agrees to a few centimetres
         assert np.abs(b.center.numpy() - host[i].center).max() < 0.15
         assert np.abs(b.rot.numpy() - host[i].rotation_matrix).max() < 1e-6
+
+
+def test_motion_input_matches_reference_restatement():
+    """MotionBaseModel.build_input_dict (M2-Track) against the numpy restatement, first and later frames."""
+    import os
+    from open3dsot_b200.config import load_config
+    from open3dsot_b200.models.base_model import MotionBaseModel
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = load_config(os.path.join(root, "cfgs", "M2_track_kitti.yaml"), {})
+    seq = synthetic_sequence(n_frames=4, n_points=5000, seed=9)
+
+    class Host(MotionBaseModel):
+        device = torch.device("cpu")
+    m = Host(cfg)
+    for frame_id in (1, 3):
+        ref = seq[frame_id - 1]["3d_bbox"]
+        data, _ = m.build_input_dict(seq, frame_id, [ref])
+        want = R.motion_build_input(seq[frame_id - 1]["pc"].points.astype(np.float64), seq[frame_id]["pc"].points.astype(np.float64),
+                                    R.Box(ref.center, ref.wlh, ref.rotation_matrix), cfg, frame_id)
+        for k in want:
+            assert data[k].shape == want[k].shape and np.abs(data[k].numpy() - want[k]).max() < 2e-5, k
+        vals = np.unique(data["points"][0, : cfg.point_sample_size, 4].numpy().astype(np.float64).round(3))
+        assert set(vals.tolist()) <= ({0.0, 1.0} if frame_id == 1 else {0.2, 0.8})
