@@ -14,5 +14,6 @@ def get_dataset(config, type='train', **kwargs):
         from .device_sampler import DeviceSiameseSampler
         return DeviceSiameseSampler(data.tracklets(), config, kwargs.get('device', 'cuda'))
     if type.lower() == 'train_motion':
-        raise NotImplementedError("motion_processing on the device is not built yet (SURVEY.md 8f rank 3, M2-Track half)")
+        from .device_sampler import DeviceMotionSampler
+        return DeviceMotionSampler(data.tracklets(), config, kwargs.get('device', 'cuda'))
     return data.tracklets()

@@ -119,13 +119,79 @@ def siamese_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=No
     return batch, (n_t > 20) & (n_s > 20)
 
 
+def in_box_inclusive(points, box: bx.Box, wlh_factor=1.0):
+    """nuscenes geometry_utils.points_in_box (used at sampler.py:130-132): its three projection tests 0 <= v.e <= e.e are the
+    inclusive form of |local| <= half * wlh_factor in the box frame."""
+    local = bx.to_box_frame(points, box)
+    half = torch.stack([box.wlh[..., 1], box.wlh[..., 0], box.wlh[..., 2]], -1)[..., None, :] * (wlh_factor / 2)
+    return (local.abs() <= half).all(-1)
+
+
+def yaw_of(rot, degrees):
+    """Signed rotation angle about +z of a (..., 3, 3) yaw rotation — pyquaternion's `degrees * axis[-1]` (sampler.py:149-156)."""
+    a = torch.atan2(rot[..., 1, 0], rot[..., 0, 0])
+    return torch.rad2deg(a) if degrees else a
+
+
+def motion_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=None, generator=None):
+    """motion_processing (sampler.py:82-181) for the frames `frame_ids` (B,): previous + current sub-windows in the frame of
+    the (randomly offset) previous box, stacked with timestamp / prior-targetness channels, segmentation labels, box /
+    previous-box / motion regression targets, motion-state label and the three BoxClouds.  Returns (batch, valid (B,))."""
+    dev = data.scans.device
+    B = frame_ids.shape[0]
+    draws = draws or {}
+    n = cfg.point_sample_size
+    deg = 5.0 if cfg.degrees else 0.08726646259971647
+    ang_scale = torch.cat([torch.ones(2, device=dev), torch.full((1,), deg, device=dev)])
+    cand0 = candidate_ids == 0
+    i_prev = data.prev[frame_ids]
+    prev_box, this_box = data.box(i_prev), data.box(frame_ids)
+    off = draws.get("offset")
+    if off is None:
+        off = torch.rand(B, 3, device=dev, generator=generator) * 0.6 - 0.3
+    off = torch.where(cand0[:, None], torch.zeros_like(off), off * ang_scale)
+    rand = draws.get("limit_rand")
+    if rand is None and cfg.data_limit_box:
+        rand = torch.rand(B, 2, device=dev, generator=generator) * 2 - 1
+    ref = bx.offset_box(prev_box, off, degrees=cfg.degrees, limit_box=cfg.data_limit_box, rand=rand)
+    # enough target points in the previous GT box (sampler.py:99-100)
+    p_gt_local, p_gt_keep = bx.crop_in_box_frame(data.scans, prev_box, 1.0, 0.0, i_prev, data.count)
+    half_gt = torch.stack([prev_box.wlh[:, 1], prev_box.wlh[:, 0], prev_box.wlh[:, 2]], -1)[:, None, :] / 2
+    n_target = ((p_gt_local.abs() <= half_gt).all(-1) & data.valid(i_prev)).sum(1)
+    p_local, p_keep = bx.crop_in_box_frame(data.scans, ref, cfg.bb_scale, cfg.bb_offset, i_prev, data.count)
+    t_local, t_keep = bx.crop_in_box_frame(data.scans, ref, cfg.bb_scale, cfg.bb_offset, frame_ids, data.count)
+    this_b, prev_b = transform_box(this_box, ref), transform_box(prev_box, ref)
+    canon = bx.Box(torch.zeros_like(ref.center), ref.wlh, torch.eye(3, device=dev).expand_as(ref.rot))
+    motion_b = transform_box(this_b, prev_b)
+    prev_pts, _, n_p = resample_batched(p_local, p_keep, n, draws.get("u_p"), draws.get("u_pick_p"), generator)
+    this_pts, _, n_t = resample_batched(t_local, t_keep, n, draws.get("u_t"), draws.get("u_pick_t"), generator)
+    seg_this = in_box_inclusive(this_pts, this_b, 1.25)
+    seg_prev = in_box_inclusive(prev_pts, prev_b, 1.25)
+    mask_prev = in_box_inclusive(prev_pts, canon, 1.25).float()
+    mask_prev = torch.where(cand0[:, None], mask_prev, mask_prev * 0.6 + 0.2)             # 0.2 / 0.8: the prior box is not GT
+    col = lambda pts, t, m: torch.cat([pts, torch.full_like(pts[..., :1], t), m[..., None]], -1)
+    points = torch.cat([col(prev_pts, 0.0, mask_prev), col(this_pts, 0.1, torch.full_like(mask_prev, 0.5))], 1)
+    lab = lambda b: torch.cat([b.center, yaw_of(b.rot, cfg.degrees)[:, None]], 1)
+    batch = {"points": points, "box_label": lab(this_b), "box_label_prev": lab(prev_b), "motion_label": lab(motion_b),
+             "motion_state_label": ((this_b.center - prev_b.center).norm(dim=1) > cfg.motion_threshold).long(),
+             "bbox_size": this_b.wlh, "seg_label": torch.cat([seg_prev, seg_this], 1).long()}
+    if cfg.get("box_aware", False):
+        cand_bc = bx.point_to_box_distance(prev_pts, canon)
+        batch.update({"prev_bc": bx.point_to_box_distance(prev_pts, prev_b), "this_bc": bx.point_to_box_distance(this_pts, this_b),
+                      "candidate_bc": torch.cat([cand_bc, torch.zeros_like(cand_bc)], 1)})
+    batch["_n_prev"], batch["_n_this"], batch["_n_target"] = n_p, n_t, n_target
+    return batch, (n_target > 10) & (n_t > 20)
+
+
 class DeviceSiameseSampler:
-    """Drop-in source of training batches: `next_batch()` returns the reference's batch dict, on the device.
+    """(`DeviceMotionSampler` below is the same class bound to `motion_batch`.)
+    Drop-in source of training batches: `next_batch()` returns the reference's batch dict, on the device.
     On CUDA the construction (≈ 340 small launches, host-bound when issued eagerly) is captured once in a CUDA graph;
     every replay draws new frames and offsets (graph-safe philox offsets of the default CUDA generator) into the same
     static output tensors — consume or copy a batch before asking for the next one."""
 
-    def __init__(self, tracklets, cfg, device, oversample=1.25, seed=0, max_points=None, use_graph=True):
+    def __init__(self, tracklets, cfg, device, oversample=1.25, seed=0, max_points=None, use_graph=True, processing=None):
+        self.processing = processing or siamese_batch           # `motion_batch` for the motion-centric models
         self.data = tracklets if isinstance(tracklets, DeviceTracklets) else DeviceTracklets(tracklets, device, max_points)
         self.cfg = cfg
         dev = self.data.scans.device
@@ -142,8 +208,8 @@ class DeviceSiameseSampler:
         pool = int(B * self.oversample) + 1
         dev = self.data.scans.device
         index = torch.randint(0, self.data.num_frames * self.num_candidates, (pool,), device=dev, generator=self.gen)
-        batch, valid = siamese_batch(self.data, self.cfg, index // self.num_candidates, index % self.num_candidates,
-                                     generator=self.gen)
+        batch, valid = self.processing(self.data, self.cfg, index // self.num_candidates, index % self.num_candidates,
+                                       generator=self.gen)
         order = torch.argsort((~valid).to(torch.int8), stable=True)[:B]       # valid samples first, original order kept
         return {k: v[order] for k, v in batch.items() if not k.startswith("_")}, valid[order]
 
@@ -164,3 +230,10 @@ class DeviceSiameseSampler:
         g, out = self._graphs[B]
         g.replay()
         return out
+
+
+class DeviceMotionSampler(DeviceSiameseSampler):
+    """MotionTrackingSampler + motion_processing (sampler.py:82-181, :262-288) on the device."""
+
+    def __init__(self, tracklets, cfg, device, **kw):
+        super().__init__(tracklets, cfg, device, processing=motion_batch, **kw)

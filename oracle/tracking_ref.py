@@ -315,3 +315,54 @@ def motion_build_input(prev_pts, this_pts, ref_box, cfg, frame_id):
         bc = get_point_to_box_distance(stack[:n, :3], canon)
         out["candidate_bc"] = np.concatenate([bc, np.zeros_like(bc)], 0)[None].astype("float32")
     return out
+
+
+def _yaw(rot, degrees):
+    a = np.arctan2(rot[1, 0], rot[0, 0])
+    return np.rad2deg(a) if degrees else a
+
+
+def _in_box_inclusive(points, box, factor):
+    """nuscenes geometry_utils.points_in_box on (N, 3) points."""
+    local = (points - box.center) @ box.rot
+    half = np.array([box.wlh[1], box.wlh[0], box.wlh[2]]) * factor / 2
+    return (np.abs(local) <= half).all(1)
+
+
+def motion_processing(prev, this, candidate_id, cfg, offset, idx_prev=None, idx_this=None, limit_rand=None):
+    """datasets/sampler.py:82-181 with the random draws passed in.  Frames are (points (3, N), Box)."""
+    (prev_pc, prev_box), (this_pc, this_box) = prev, this
+    n = cfg["point_sample_size"]
+    deg = 5 if cfg["degrees"] else np.deg2rad(5)
+    n_target = int(_in_box_inclusive(prev_pc.T, prev_box, 1.0).sum())
+    if candidate_id == 0:
+        off = np.zeros(3)
+    else:
+        off = np.array(offset, dtype=np.float64)
+        off[2] = off[2] * deg
+    ref = get_offset_bb(prev_box, off, limit_box=cfg["data_limit_box"], degrees=cfg["degrees"], rand=limit_rand)
+    prev_crop = generate_subwindow(prev_pc, ref, cfg["bb_scale"], cfg["bb_offset"])
+    this_crop = generate_subwindow(this_pc, ref, cfg["bb_scale"], cfg["bb_offset"])
+    this_b, prev_b, ref_b = transform_box(this_box, ref), transform_box(prev_box, ref), transform_box(ref, ref)
+    motion_b = transform_box(this_b, prev_b)
+    pp = prev_crop.T[idx_prev] if idx_prev is not None else regularize_pc(prev_crop.T, n)[0]
+    tp = this_crop.T[idx_this] if idx_this is not None else regularize_pc(this_crop.T, n)[0]
+    seg_this = _in_box_inclusive(tp, this_b, 1.25).astype(int)
+    seg_prev = _in_box_inclusive(pp, prev_b, 1.25).astype(int)
+    mask_prev = _in_box_inclusive(pp, ref_b, 1.25).astype(float)
+    if candidate_id != 0:
+        mask_prev = np.where(mask_prev == 0, 0.2, 0.8)
+    stack = np.concatenate([np.concatenate([pp, np.full((n, 1), 0.0), mask_prev[:, None]], -1),
+                            np.concatenate([tp, np.full((n, 1), 0.1), np.full((n, 1), 0.5)], -1)], 0)
+    lab = lambda b: np.append(b.center, _yaw(b.rot, cfg["degrees"])).astype("float32")
+    out = {"points": stack.astype("float32"), "box_label": lab(this_b), "box_label_prev": lab(prev_b), "motion_label": lab(motion_b),
+           "motion_state_label": int(np.sqrt(((this_b.center - prev_b.center) ** 2).sum()) > cfg["motion_threshold"]),
+           "bbox_size": this_b.wlh, "seg_label": np.hstack([seg_prev, seg_this]).astype(int),
+           "n_prev": prev_crop.shape[1], "n_this": this_crop.shape[1], "n_target": n_target,
+           "_prev_crop": prev_crop, "_this_crop": this_crop, "_boxes": (this_b, prev_b, ref_b)}
+    if cfg.get("box_aware", False):
+        c = get_point_to_box_distance(pp, ref_b)
+        out.update({"prev_bc": get_point_to_box_distance(pp, prev_b).astype("float32"),
+                    "this_bc": get_point_to_box_distance(tp, this_b).astype("float32"),
+                    "candidate_bc": np.concatenate([c, np.zeros_like(c)], 0).astype("float32")})
+    return out

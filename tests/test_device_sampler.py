@@ -75,3 +75,55 @@ def test_sampler_returns_reference_batch_schema():
     assert all(v.dtype == torch.float32 for v in batch.values())
     b2, _ = smp.next_batch()
     assert not torch.equal(b2["search_points"], batch["search_points"])      # a new draw every call
+
+
+def test_motion_batch_matches_reference_restatement():
+    from open3dsot_b200.datasets.device_sampler import DeviceMotionSampler, motion_batch
+    cfg = load_config(os.path.join(ROOT, "cfgs", "M2_track_kitti.yaml"), {})
+    tracklets = [synthetic_sequence(n_frames=4, n_points=3000, seed=31 + i, n_object=400) for i in range(2)]
+    data = DeviceTracklets(tracklets, "cpu")
+    frames = [f for t in tracklets for f in t]
+    B = 8
+    g = torch.Generator().manual_seed(6)
+    frame_ids, cand = torch.arange(B), torch.tensor([0, 1, 2, 3, 0, 1, 2, 3])
+    draws = {"offset": torch.rand(B, 3, generator=g) * 0.6 - 0.3, "limit_rand": torch.rand(B, 2, generator=g) * 2 - 1}
+    batch, valid = motion_batch(data, cfg, frame_ids, cand, draws=draws, generator=g)
+    assert bool(valid.all())
+    n = cfg.point_sample_size
+
+    def fr(f):
+        bb = f["3d_bbox"]
+        return f["pc"].points.astype(np.float64), R.Box(bb.center, bb.wlh, bb.rotation_matrix)
+
+    for b in range(B):
+        k = int(frame_ids[b])
+        want = R.motion_processing(fr(frames[int(data.prev[k])]), fr(frames[k]), int(cand[b]), cfg, draws["offset"][b].double().numpy(),
+                                   limit_rand=draws["limit_rand"][b].tolist())
+        assert (int(batch["_n_prev"][b]), int(batch["_n_this"][b]), int(batch["_n_target"][b])) == (want["n_prev"], want["n_this"], want["n_target"])
+        for key in ("box_label", "box_label_prev", "motion_label", "bbox_size"):
+            assert np.abs(batch[key][b].numpy() - want[key]).max() < 2e-4, key
+        assert int(batch["motion_state_label"][b]) == want["motion_state_label"]
+        pts = batch["points"][b].numpy()
+        ok_p, _ = _rows_in(pts[:n, :3], want["_prev_crop"].T)
+        ok_t, _ = _rows_in(pts[n:, :3], want["_this_crop"].T)
+        assert ok_p and ok_t
+        assert np.all(pts[:n, 3] == 0) and np.allclose(pts[n:, 3], 0.1) and np.allclose(pts[n:, 4], 0.5)
+        this_b, prev_b, ref_b = want["_boxes"]
+        # labels recomputed by the restatement on the device's own (different random) subset
+        seg = np.hstack([R._in_box_inclusive(pts[:n, :3].astype(np.float64), prev_b, 1.25), R._in_box_inclusive(pts[n:, :3].astype(np.float64), this_b, 1.25)])
+        flips = int((batch["seg_label"][b].numpy().astype(bool) != seg).sum())
+        assert flips <= 2                                                      # float32 vs float64 on the box faces
+        m = R._in_box_inclusive(pts[:n, :3].astype(np.float64), ref_b, 1.25).astype(float)
+        if int(cand[b]) != 0:
+            m = np.where(m == 0, 0.2, 0.8)
+        assert int((np.abs(pts[:n, 4] - m) > 1e-6).sum()) <= 2
+        assert np.abs(batch["prev_bc"][b].numpy() - R.get_point_to_box_distance(pts[:n, :3].astype(np.float64), prev_b)).max() < 1e-4
+        assert np.abs(batch["this_bc"][b].numpy() - R.get_point_to_box_distance(pts[n:, :3].astype(np.float64), this_b)).max() < 1e-4
+        assert np.abs(batch["candidate_bc"][b, :n].numpy() - R.get_point_to_box_distance(pts[:n, :3].astype(np.float64), ref_b)).max() < 1e-4
+        assert float(batch["candidate_bc"][b, n:].abs().sum()) == 0
+
+    smp = DeviceMotionSampler(tracklets, load_config(os.path.join(ROOT, "cfgs", "M2_track_kitti.yaml"), {"batch_size": 4}), "cpu", seed=2)
+    out, valid = smp.next_batch()
+    from open3dsot_b200.datasets.synthetic import synthetic_motion_batch
+    ref = synthetic_motion_batch(4, cfg.point_sample_size)
+    assert {k: (tuple(v.shape), v.dtype) for k, v in out.items()} == {k: (tuple(v.shape), v.dtype) for k, v in ref.items()}
