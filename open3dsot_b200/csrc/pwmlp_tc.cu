@@ -1,7 +1,7 @@
 // Tensor-core (tcgen05 / TMEM) implementation of the point-wise MLP forward and data-gradient GEMMs, 3xTF32.
 //
 // Same contract as pw_fwd_kernel / pw_dgrad_kernel in pwmlp.cu (which remain the exact-fp32 ground truth and
-// serve the shapes this kernel does not take: K < 32, fewer than 128 output channels, ragged channel counts).
+// serve the shapes this kernel does not take: K < 32, ragged channel tails, very small P).
 //
 //   D[ch, pos] = sum_k  Wmat[ch, k] * Act[pos, k]          ch tile = 128 (UMMA M), pos tile = 128 (UMMA N)
 //
@@ -10,18 +10,21 @@
 // (x - hi, exact), so that   Whi*Xhi + Wlo*Xhi + Whi*Xlo   carries ~21 mantissa bits — fp32-grade accuracy, which
 // the 1e-4 parity bar needs and a single TF32 pass (10 bits) cannot give.
 //
-// Roles (384 threads, one persistent CTA per SM, all roles walk the same static tile sequence):
-//   warp 0      allocates TMEM (2 x 128 fp32 columns: double-buffered accumulator) and, one elected lane, issues
-//               tcgen05.mma.cta_group::1.kind::tf32 (M128 N128 K8), 12 per 32-channel k-block, committing each
-//               stage back to the producers and each finished tile to the epilogue through mbarriers
-//   warp 1      one lane streams the pre-tiled, pre-swizzled weight images (hi|lo, 32 KB per k-block) with
-//               cp.async.bulk (UBLKCP) onto the stage's "full" barrier
-//   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns; lane = output channel, columns = positions, so the
-//               batch statistics, the group max/min/arg and the ReLU-mask sums are plain per-thread loops and every
-//               global store of a warp is one coalesced 128-byte line
-//   warps 8-11  operand producers: coalesced 16-byte loads, transform, hi/lo split, 128B-swizzled st.shared,
-//               fence.proxy.async, arrive
-// Shared memory: 3 stages x (W_hi 16K | W_lo 16K | X_hi 16K | X_lo 16K) = 192 KB, K-major SWIZZLE_128B tiles.
+// Roles of pw_tc_kernel (576 threads = 18 warps, one persistent CTA per SM, all roles walk the same static tile sequence):
+//   warp 0        allocates TMEM (double-buffered accumulators: 2 x MT x 128 fp32 columns) and, one elected lane, issues
+//                 tcgen05.mma.cta_group::1.kind::tf32 (M128 N128 K8), 12 per 32-channel k-block and channel tile, committing
+//                 each stage back to the producers and each finished tile to the epilogue through mbarriers
+//   warp 1        one lane streams the pre-tiled, pre-swizzled weight images (hi|lo, 32 KB per k-block and channel tile,
+//                 written once per call by stack.cu's pack kernel) with cp.async.bulk (UBLKCP) onto the stage's "full"
+//                 barrier, and asks for the next position tile's rows with cp.async.bulk.prefetch.L2
+//   warps 4-11    epilogue: tcgen05.ld 32 lanes x 16 columns; lane = output channel, columns = positions, so the batch
+//                 statistics, the group max/min/arg and the ReLU-mask sums are plain per-thread loops and every global
+//                 store of a warp is one coalesced 128-byte line (MT = 2: one warp group per channel tile;
+//                 MT = 1: the two groups split the columns)
+//   warps 2,3,12-17  operand producers (256 threads, 4 neighbouring rows each): coalesced 16-byte loads issued one
+//                 k-block ahead ("raw-first"), transform, hi/lo split, 128B-swizzled st.shared, fence.proxy.async, arrive
+// Shared memory: MT = 1: 3 stages x (W 32K | X 32K) = 192 KB;  MT = 2: 2 stages x (W 64K | X 32K) = 192 KB; K-major
+// SWIZZLE_128B tiles.  The wgrad kernels further down have their own role tables.
 #include "common.cuh"
 #include "../../include/o3d_b200.h"
 
