@@ -142,6 +142,8 @@ def track_cpu_baseline(cfg, seq, frames):
     torch.manual_seed(0)
     net = get_model(cfg.net_model)(cfg).eval()
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    if cfg.net_model.lower() not in ("bat", "p2b"):
+        return None                                  # the oracle restates the matching models' forward only
     fwd = om.bat_forward if cfg.net_model.lower() == "bat" else om.p2b_forward
     boxes = [tr.Box(seq[0]["3d_bbox"].center, seq[0]["3d_bbox"].wlh, seq[0]["3d_bbox"].rotation_matrix)]
     times = []

@@ -22,6 +22,7 @@ class DeviceTracker:
         self.use_graph = bool(use_graph) and self.dev.type == "cuda"
         self.gen = torch.Generator(device=self.dev).manual_seed(seed)
         self.needs_bc = hasattr(model, "mlp_bc")            # BAT consumes the template BoxCloud
+        self.motion = "point_sample_size" in self.cfg and not hasattr(model, "backbone")   # M2-Track style two-frame input
         f = dict(device=self.dev, dtype=torch.float32)
         n = self.max_points
         # static buffers (graph inputs / state)
@@ -35,8 +36,11 @@ class DeviceTracker:
         self.box_s = torch.ones(3, **f)
         self.box_r = torch.eye(3, **f)
         # uniform draws of the two resamplings: refreshed per frame OUTSIDE the captured graph (seeded, reproducible)
-        self.u_s = (torch.zeros(n, **f), torch.zeros(self.cfg.search_size, **f))
-        self.u_t = (torch.zeros(2 * n, **f), torch.zeros(self.cfg.template_size, **f))
+        size_s = self.cfg.point_sample_size if self.motion else self.cfg.search_size
+        size_t = self.cfg.point_sample_size if self.motion else self.cfg.template_size
+        self.u_s = (torch.zeros(n, **f), torch.zeros(size_s, **f))
+        self.u_t = (torch.zeros(2 * n, **f), torch.zeros(size_t, **f))
+        self.first_flag = torch.ones((), **f)               # 1 on the first tracked frame (prior box = ground truth), then 0
         self.graph = None
         self.frames = 0
 
@@ -58,16 +62,41 @@ class DeviceTracker:
         self._load_scan(points)
         box = box.to(self.dev)
         self.box_c.copy_(box.center); self.box_s.copy_(box.wlh); self.box_r.copy_(box.rot)
-        local, keep, _ = bx.crop_and_center(self.scan, box, offset=self.cfg.model_bb_offset, scale=self.cfg.model_bb_scale)
-        self.first_local.copy_(local)
-        self.first_keep.copy_(keep & self.scan_valid)
+        if not self.motion:
+            local, keep, _ = bx.crop_and_center(self.scan, box, offset=self.cfg.model_bb_offset, scale=self.cfg.model_bb_scale)
+            self.first_local.copy_(local)
+            self.first_keep.copy_(keep & self.scan_valid)
+        self.first_flag.fill_(1.0)
         self.prev_scan.copy_(self.scan)
         self.prev_valid.copy_(self.scan_valid)
         self.frames = 1
         return self._box()
 
     # ------------------------------------------------------------------ one frame, fixed shapes
+    def _inputs_motion(self):
+        """MotionBaseModel.build_input_dict (models/base_model.py:255-303) on static buffers."""
+        cfg, box = self.cfg, self._box()
+        b1 = bx.Box(box.center[None], box.wlh[None], box.rot[None])
+        n = cfg.point_sample_size
+        p_local, p_keep = bx.crop_in_box_frame(self.prev_scan[None], b1, cfg.bb_scale, cfg.bb_offset)
+        t_local, t_keep = bx.crop_in_box_frame(self.scan[None], b1, cfg.bb_scale, cfg.bb_offset)
+        prev_pts, _ = resample(p_local[0], p_keep[0] & self.prev_valid, n, u_perm=self.u_t[0][: self.max_points], u_pick=self.u_t[1])
+        this_pts, _ = resample(t_local[0], t_keep[0] & self.scan_valid, n, u_perm=self.u_s[0], u_pick=self.u_s[1])
+        half = torch.stack([box.wlh[1], box.wlh[0], box.wlh[2]]) * (1.25 / 2)
+        inside = (prev_pts.abs() <= half).all(-1).float()
+        f = self.first_flag
+        mask_prev = inside * (0.6 + 0.4 * f) + 0.2 * (1 - f)               # 1 / 0 on the first frame, 0.8 / 0.2 afterwards
+        col = lambda pts, t, m: torch.cat([pts, torch.full_like(pts[:, :1], t), m[:, None]], -1)
+        data = {"points": torch.cat([col(prev_pts, 0.0, mask_prev), col(this_pts, 0.1, torch.full_like(mask_prev, 0.5))], 0)[None]}
+        if getattr(cfg, "box_aware", False):
+            canon = bx.Box(torch.zeros_like(box.center), box.wlh, torch.eye(3, device=self.dev))
+            bc = bx.point_to_box_distance(prev_pts, canon)
+            data["candidate_bc"] = torch.cat([bc, torch.zeros_like(bc)], 0)[None]
+        return data
+
     def _inputs(self):
+        if self.motion:
+            return self._inputs_motion()
         cfg, box = self.cfg, self._box()
         # search area: current scan in the frame of the reference box (= previous result)
         b1 = bx.Box(box.center[None], box.wlh[None], box.rot[None])
@@ -103,6 +132,7 @@ class DeviceTracker:
             new = bx.offset_box(self._box(), est, degrees=cfg.degrees, use_z=cfg.use_z, limit_box=cfg.limit_box)
             self.box_c.copy_(new.center); self.box_r.copy_(new.rot)
             self.prev_scan.copy_(self.scan); self.prev_valid.copy_(self.scan_valid)
+            self.first_flag.zero_()
 
     def step(self, points, n_valid=None):
         """Next frame: `points` (n, 3) device tensor.  Returns the tracked box (views of the tracker's state buffers)."""
@@ -114,18 +144,19 @@ class DeviceTracker:
         if not self.use_graph:
             self._frame()
         elif self.graph is None:
-            snap = [t.clone() for t in (self.box_c, self.box_r, self.prev_scan, self.prev_valid)]
+            state = (self.box_c, self.box_r, self.prev_scan, self.prev_valid, self.first_flag)
+            snap = [t.clone() for t in state]
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 self._frame()                                                   # warm-up (allocations, autotuning)
             torch.cuda.current_stream().wait_stream(s)
-            for t, v in zip((self.box_c, self.box_r, self.prev_scan, self.prev_valid), snap):
+            for t, v in zip(state, snap):
                 t.copy_(v)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._frame()
-            for t, v in zip((self.box_c, self.box_r, self.prev_scan, self.prev_valid), snap):
+            for t, v in zip(state, snap):
                 t.copy_(v)
             self.graph.replay()
         else:

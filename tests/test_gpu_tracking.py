@@ -49,9 +49,10 @@ def test_host_loop_and_device_tracker_run_the_network(cfg_name):
         assert float((res[graph][-1][0] - start).norm()) < 50.0
 
 
-def test_graph_replay_equals_eager_frames():
+@pytest.mark.parametrize("cfg_name", ["BAT_Car.yaml", "M2_track_kitti.yaml"])
+def test_graph_replay_equals_eager_frames(cfg_name):
     """Same seed -> same resampling draws -> the captured frame and the eager frame produce the same boxes."""
-    cfg, net = _model("BAT_Car.yaml")
+    cfg, net = _model(cfg_name)
     seq = synthetic_sequence(n_frames=5, n_points=8000, seed=3)
     pts = [torch.tensor(f["pc"].points.T.copy(), device="cuda") for f in seq]
     tracks = []

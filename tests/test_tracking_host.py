@@ -202,3 +202,43 @@ def test_motion_input_matches_reference_restatement():
             assert data[k].shape == want[k].shape and np.abs(data[k].numpy() - want[k]).max() < 2e-5, k
         vals = np.unique(data["points"][0, : cfg.point_sample_size, 4].numpy().astype(np.float64).round(3))
         assert set(vals.tolist()) <= ({0.0, 1.0} if frame_id == 1 else {0.2, 0.8})
+
+
+def test_device_tracker_motion_mode_inputs():
+    """M2-Track style two-frame input on the tracker's static buffers: channel layout, prior-targetness values (1/0 on the
+    first tracked frame, 0.8/0.2 afterwards) and the BoxCloud halves."""
+    from open3dsot_b200.models.base_model import MotionBaseModel
+    cfg = EasyDict(point_sample_size=256, bb_scale=1.25, bb_offset=2, box_aware=True, degrees=False, use_z=True, limit_box=False,
+                   IoU_space=3, up_axis=[0, 0, 1])
+
+    class Stub(MotionBaseModel):
+        def __init__(self, c):
+            super().__init__(c)
+            self.dummy = torch.nn.Parameter(torch.zeros(1))
+            self.seen = []
+
+        @property
+        def device(self):
+            return self.dummy.device
+
+        def forward(self, d):
+            self.seen.append({k: v.clone() for k, v in d.items()})
+            return {"estimation_boxes": torch.tensor([[0.55, 0.0, 0.0, 0.02]])}
+    m = Stub(cfg)
+    seq = synthetic_sequence(n_frames=4, n_points=4000, seed=17)
+    trk = DeviceTracker(m, max_points=4000, use_graph=False)
+    assert trk.motion
+    pts = [torch.tensor(f["pc"].points.T.copy()) for f in seq]
+    trk.reset(pts[0], seq[0]["3d_bbox"].to_tensor())
+    for i in range(1, 4):
+        b = trk.step(pts[i])
+    n = cfg.point_sample_size
+    for i, d in enumerate(m.seen):
+        p = d["points"][0]
+        assert p.shape == (2 * n, 5) and d["candidate_bc"].shape == (1, 2 * n, 9)
+        assert float(p[:n, 3].abs().sum()) == 0 and torch.allclose(p[n:, 3], torch.full((n,), 0.1)) and torch.allclose(p[n:, 4], torch.full((n,), 0.5))
+        vals = set(p[:n, 4].double().round(decimals=3).unique().tolist())
+        assert vals <= ({0.0, 1.0} if i == 0 else {0.2, 0.8}) and len(vals) == 2
+        assert float(d["candidate_bc"][0, n:].abs().sum()) == 0 and float(d["candidate_bc"][0, :n].min()) > 0
+    _, _, host = m.evaluate_one_sequence(seq)                    # the reference-shaped loop with the same constant offsets
+    assert np.abs(b.center.numpy() - host[3].center).max() < 1e-4
