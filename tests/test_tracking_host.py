@@ -242,3 +242,32 @@ def test_device_tracker_motion_mode_inputs():
         assert float(d["candidate_bc"][0, n:].abs().sum()) == 0 and float(d["candidate_bc"][0, :n].min()) > 0
     _, _, host = m.evaluate_one_sequence(seq)                    # the reference-shaped loop with the same constant offsets
     assert np.abs(b.center.numpy() - host[3].center).max() < 1e-4
+
+
+def test_points_utils_names_match_the_restatement():
+    """datasets/points_utils.py under the reference's names and signatures (host containers in, host containers out)."""
+    from open3dsot_b200.datasets import points_utils as PU
+    rng, ob, tb, pts = _pair(3)
+    pc, hb = dc.PointCloud(pts.copy()), dc.Box(ob.center, ob.wlh, ob.rot)
+    want, wbox = R.crop_and_center_pc(pts, ob, offset=0.2, scale=1.25)
+    got, gbox = PU.cropAndCenterPC(pc, hb, offset=0.2, scale=1.25)
+    assert got.points.shape == want.shape and np.abs(got.points - want).max() < 1e-12 and np.abs(gbox.center).max() < 1e-12
+    assert np.abs(PU.generate_subwindow(pc, hb, 1.25, 2).points - R.generate_subwindow(pts, ob, 1.25, 2)).max() < 1e-12
+    w2, _ = R.crop_pc_axis_aligned(pts, ob, offset=0.5, scale=1.1)
+    g2, mask = PU.crop_pc_axis_aligned(pc, hb, offset=0.5, scale=1.1, return_mask=True)
+    assert np.array_equal(g2.points, w2) and int(mask.sum()) == w2.shape[1]
+    ob2 = R.get_offset_bb(ob, [0.3, 0.1, 0.0, 7.0], use_z=True, limit_box=False)
+    hb2 = PU.getOffsetBB(hb, [0.3, 0.1, 0.0, 7.0], use_z=True, limit_box=False)
+    assert np.abs(hb2.center - ob2.center).max() < 1e-12 and np.abs(hb2.rotation_matrix - ob2.rot).max() < 1e-12
+    wm, wb = R.get_model([pts, pts + 0.01], [ob, ob2], offset=0, scale=1.25)
+    gm, gb = PU.getModel([pc, dc.PointCloud(pts + 0.01)], [hb, hb2], offset=0, scale=1.25)
+    assert gm.points.shape == wm.shape and np.abs(gm.points - wm).max() < 1e-12
+    assert np.abs(PU.get_point_to_box_distance(pts.T[:50], hb) - R.get_point_to_box_distance(pts.T[:50], ob)).max() < 1e-12
+    tbx = PU.transform_box(hb2, hb)
+    wtb = R.transform_box(ob2, ob)
+    assert np.abs(tbx.center - wtb.center).max() < 1e-12 and np.abs(tbx.rotation_matrix - wtb.rot).max() < 1e-12
+    assert np.array_equal(PU.get_in_box_mask(pc, hb), R.get_in_box_mask(pts, ob))
+    assert np.abs(PU.transform_pc(pc, hb).points - ob.rot.T @ (pts - ob.center[:, None])).max() < 1e-12
+    p, i = PU.regularize_pc(pts.T, 128, seed=1)
+    wp, wi = R.regularize_pc(pts.T, 128, seed=1)
+    assert np.array_equal(i, wi) and np.array_equal(p, wp)
