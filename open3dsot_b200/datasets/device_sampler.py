@@ -66,6 +66,21 @@ def in_box_mask(points, box: bx.Box):
     return (local.abs() < half).all(-1)
 
 
+def _augment(data, cfg, idx, box, draws, key, generator):
+    """The reference's optional `apply_augmentation` transform on the frames `idx` (sampler.py:31-35 / :102-105):
+    returns (scans (B, N, 3) or None when augmentation is off, per-sample valid counts, box)."""
+    if not cfg.get("use_augmentation", False):
+        return None, None, box
+    dev = data.scans.device
+    B = idx.shape[0]
+    d = (draws or {}).get(key)
+    if d is None:
+        u = torch.rand(B, 6, device=dev, generator=generator)
+        d = {"trans": u[:, :3] * 0.6 - 0.3, "rot": u[:, 3] * 20 - 10, "flip_x": u[:, 4] < 0.5, "flip_y": u[:, 5] < 0.5}
+    pts, box = apply_augmentation(data.scans[idx], box, d["trans"], d["rot"], d["flip_x"], d["flip_y"], data.valid(idx))
+    return pts, data.count[idx], box
+
+
 def siamese_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=None, generator=None):
     """siamese_processing for the frames `frame_ids` (B,) with candidate indices `candidate_ids` (B,).
     `draws` may carry explicit random numbers (tests): 'template_offset' (B, 3) uniform(-0.3, 0.3) draws, 'search_offset'
@@ -103,9 +118,12 @@ def siamese_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=No
     off_s = off_s * ang_scale.sqrt()            # N(0, diag(1, 1, 5 deg)): KalmanFiltering.reset
     if cfg.get("num_candidates", 1) > 1:
         off_s = torch.where(cand0[:, None], torch.zeros_like(off_s), off_s)
-    gt = data.box(frame_ids)
+    aug_pts, aug_count, gt = _augment(data, cfg, frame_ids, data.box(frame_ids), draws, "aug_search", generator)
     sample_bb = bx.offset_box(gt, off_s, degrees=cfg.degrees, limit_box=cfg.data_limit_box, rand=limit_rand("limit_rand_s"))
-    s_local, s_keep = bx.crop_in_box_frame(data.scans, sample_bb, cfg.search_bb_scale, cfg.search_bb_offset, frame_ids, data.count)
+    if aug_pts is None:
+        s_local, s_keep = bx.crop_in_box_frame(data.scans, sample_bb, cfg.search_bb_scale, cfg.search_bb_offset, frame_ids, data.count)
+    else:
+        s_local, s_keep = bx.crop_in_box_frame(aug_pts, sample_bb, cfg.search_bb_scale, cfg.search_bb_offset, None, aug_count)
     s_box = transform_box(gt, sample_bb)
     search, src, n_s = resample_batched(s_local, s_keep, cfg.search_size, draws.get("u_s"), draws.get("u_pick_s"), generator)
     seg = in_box_mask(search, s_box).float()
@@ -117,6 +135,26 @@ def siamese_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=No
         batch["points2cc_dist_s"] = bx.point_to_box_distance(search, s_box)
     batch["_n_template"], batch["_n_search"] = n_t, n_s          # survivor counts (diagnostics; dropped by next_batch)
     return batch, (n_t > 20) & (n_s > 20)
+
+
+def apply_augmentation(points, box: bx.Box, trans, rot_deg, flip_x, flip_y, valid=None, wlh_factor=1.25):
+    """points_utils.apply_augmentation / apply_transform (:303-362), batched: the points inside the 1.25x box move rigidly
+    with it — mirror in the box frame (x: the box also turns by 180 degrees so that +x stays the heading; y), rotate by
+    `rot_deg` about the box's z, shift by `trans` (box frame) — everything else stays.  points (B, N, 3), trans (B, 3),
+    rot_deg (B,), flip_x / flip_y (B,) bool.  Returns (points, box)."""
+    inside = in_box_inclusive(points, box, wlh_factor)
+    if valid is not None:
+        inside = inside & valid
+    local = bx.to_box_frame(points, box)
+    sx = torch.where(flip_x, -1.0, 1.0).to(points.dtype)
+    sy = torch.where(flip_y, -1.0, 1.0).to(points.dtype)
+    local = local * torch.stack([sx, sy, torch.ones_like(sx)], -1)[:, None, :]
+    rz = bx.rotz(rot_deg.to(points.dtype), degrees=True)
+    local = local @ rz.transpose(-1, -2) + trans[:, None, :]
+    moved = bx.from_box_frame(local, box)
+    turn = bx.rotz(torch.where(flip_x, 180.0, 0.0).to(points.dtype), degrees=True)
+    new_box = bx.Box(box.center + (box.rot @ trans[..., None])[..., 0], box.wlh, box.rot @ rz @ turn)
+    return torch.where(inside[..., None], moved, points), new_box
 
 
 def in_box_inclusive(points, box: bx.Box, wlh_factor=1.0):
@@ -145,7 +183,8 @@ def motion_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=Non
     ang_scale = torch.cat([torch.ones(2, device=dev), torch.full((1,), deg, device=dev)])
     cand0 = candidate_ids == 0
     i_prev = data.prev[frame_ids]
-    prev_box, this_box = data.box(i_prev), data.box(frame_ids)
+    prev_aug, prev_cnt, prev_box = _augment(data, cfg, i_prev, data.box(i_prev), draws, "aug_prev", generator)
+    this_aug, this_cnt, this_box = _augment(data, cfg, frame_ids, data.box(frame_ids), draws, "aug_this", generator)
     off = draws.get("offset")
     if off is None:
         off = torch.rand(B, 3, device=dev, generator=generator) * 0.6 - 0.3
@@ -155,11 +194,16 @@ def motion_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=Non
         rand = torch.rand(B, 2, device=dev, generator=generator) * 2 - 1
     ref = bx.offset_box(prev_box, off, degrees=cfg.degrees, limit_box=cfg.data_limit_box, rand=rand)
     # enough target points in the previous GT box (sampler.py:99-100)
-    p_gt_local, p_gt_keep = bx.crop_in_box_frame(data.scans, prev_box, 1.0, 0.0, i_prev, data.count)
+    def crop(aug, cnt, idx, box, scale, offset):
+        if aug is None:
+            return bx.crop_in_box_frame(data.scans, box, scale, offset, idx, data.count)
+        return bx.crop_in_box_frame(aug, box, scale, offset, None, cnt)
+    # the reference counts the target points BEFORE the augmentation (sampler.py:99-100, on the original frame)
+    p_gt_local, p_gt_keep = bx.crop_in_box_frame(data.scans, data.box(i_prev), 1.0, 0.0, i_prev, data.count)
     half_gt = torch.stack([prev_box.wlh[:, 1], prev_box.wlh[:, 0], prev_box.wlh[:, 2]], -1)[:, None, :] / 2
     n_target = ((p_gt_local.abs() <= half_gt).all(-1) & data.valid(i_prev)).sum(1)
-    p_local, p_keep = bx.crop_in_box_frame(data.scans, ref, cfg.bb_scale, cfg.bb_offset, i_prev, data.count)
-    t_local, t_keep = bx.crop_in_box_frame(data.scans, ref, cfg.bb_scale, cfg.bb_offset, frame_ids, data.count)
+    p_local, p_keep = crop(prev_aug, prev_cnt, i_prev, ref, cfg.bb_scale, cfg.bb_offset)
+    t_local, t_keep = crop(this_aug, this_cnt, frame_ids, ref, cfg.bb_scale, cfg.bb_offset)
     this_b, prev_b = transform_box(this_box, ref), transform_box(prev_box, ref)
     canon = bx.Box(torch.zeros_like(ref.center), ref.wlh, torch.eye(3, device=dev).expand_as(ref.rot))
     motion_b = transform_box(this_b, prev_b)

@@ -256,11 +256,13 @@ def get_in_box_mask(points, box):
 
 
 def siamese_processing(first, template, search, candidate_id, cfg, template_offset, search_offset, idx_t=None, idx_s=None,
-                       limit_rand_t=None, limit_rand_s=None):
+                       limit_rand_t=None, limit_rand_s=None, aug_search=None):
     """datasets/sampler.py:16-79 with the random draws passed in: `template_offset` = the uniform(-0.3, 0.3) triple,
     `search_offset` = the KalmanFiltering sample; `idx_t` / `idx_s` = regularize_pc's index draws.
     Frames are (points (3, N), Box).  Returns the data dict plus the survivor counts."""
     (first_pc, first_box), (t_pc, t_box), (s_pc, s_box) = first, template, search
+    if aug_search is not None:                                     # search_transform (sampler.py:34-35)
+        s_pc, s_box = apply_augmentation(s_pc, s_box, *aug_search)
     deg = 5 if cfg["degrees"] else np.deg2rad(5)
     if candidate_id == 0:
         off_t = np.zeros(3)
@@ -329,12 +331,18 @@ def _in_box_inclusive(points, box, factor):
     return (np.abs(local) <= half).all(1)
 
 
-def motion_processing(prev, this, candidate_id, cfg, offset, idx_prev=None, idx_this=None, limit_rand=None):
-    """datasets/sampler.py:82-181 with the random draws passed in.  Frames are (points (3, N), Box)."""
+def motion_processing(prev, this, candidate_id, cfg, offset, idx_prev=None, idx_this=None, limit_rand=None, aug_prev=None,
+                      aug_this=None):
+    """datasets/sampler.py:82-181 with the random draws passed in.  Frames are (points (3, N), Box); `aug_prev` / `aug_this`
+    = (trans, rot_deg, flip_x, flip_y) of the optional augmentation transform (:102-105)."""
     (prev_pc, prev_box), (this_pc, this_box) = prev, this
     n = cfg["point_sample_size"]
     deg = 5 if cfg["degrees"] else np.deg2rad(5)
     n_target = int(_in_box_inclusive(prev_pc.T, prev_box, 1.0).sum())
+    if aug_prev is not None:
+        prev_pc, prev_box = apply_augmentation(prev_pc, prev_box, *aug_prev)
+    if aug_this is not None:
+        this_pc, this_box = apply_augmentation(this_pc, this_box, *aug_this)
     if candidate_id == 0:
         off = np.zeros(3)
     else:
@@ -366,3 +374,31 @@ def motion_processing(prev, this, candidate_id, cfg, offset, idx_prev=None, idx_
                     "this_bc": get_point_to_box_distance(tp, this_b).astype("float32"),
                     "candidate_bc": np.concatenate([c, np.zeros_like(c)], 0).astype("float32")})
     return out
+
+
+def apply_augmentation(points, box, trans, rot_deg, flip_x, flip_y, wlh_factor=1.25):
+    """points_utils.py:303-362 (apply_transform + apply_augmentation) with the random draws passed in; points (3, N)."""
+    inside = _in_box_inclusive(points.T, box, wlh_factor)
+    rot, c = box.rot.copy(), box.center.copy()
+    new_box = copy.deepcopy(box)
+    pts = points[:, inside].copy()
+    pts = rot.T @ (pts - c[:, None])
+    new_box.translate(-c)
+    new_box.rotate(rot.T)
+    if flip_x:
+        pts[0] = -pts[0]
+        new_box.rotate(rotz(180.0))
+    if flip_y:
+        pts[1] = -pts[1]
+    q = rotz(rot_deg)
+    new_box.rotate(q)
+    pts = q @ pts
+    new_box.translate(np.asarray(trans, dtype=np.float64))
+    pts = pts + np.asarray(trans, dtype=np.float64)[:, None]
+    new_box.rotate(rot)
+    pts = rot @ pts
+    new_box.translate(c)
+    pts = pts + c[:, None]
+    out = points.copy()
+    out[:, inside] = pts
+    return out, new_box

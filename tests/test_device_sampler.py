@@ -20,9 +20,9 @@ def _rows_in(rows, pool, tol=2e-5):
     return d.min(1).max() < tol, d.argmin(1)
 
 
-@pytest.mark.parametrize("cfg_name", ["BAT_Car.yaml", "P2B_Car.yaml"])
-def test_batch_matches_reference_restatement(cfg_name):
-    cfg = load_config(os.path.join(ROOT, "cfgs", cfg_name), {})
+@pytest.mark.parametrize("cfg_name,augment", [("BAT_Car.yaml", False), ("P2B_Car.yaml", False), ("BAT_Car.yaml", True)])
+def test_batch_matches_reference_restatement(cfg_name, augment):
+    cfg = load_config(os.path.join(ROOT, "cfgs", cfg_name), {"use_augmentation": augment})
     tracklets = [synthetic_sequence(n_frames=4, n_points=3000, seed=21 + i, n_object=400) for i in range(2)]
     data = DeviceTracklets(tracklets, "cpu")
     frames = [f for t in tracklets for f in t]
@@ -32,6 +32,9 @@ def test_batch_matches_reference_restatement(cfg_name):
     cand = torch.tensor([0, 1, 2, 3, 0, 1, 2, 3])
     draws = {"template_offset": torch.rand(B, 3, generator=g) * 0.6 - 0.3, "search_offset": torch.randn(B, 3, generator=g) * 0.6,
              "limit_rand_t": torch.rand(B, 2, generator=g) * 2 - 1, "limit_rand_s": torch.rand(B, 2, generator=g) * 2 - 1}
+    if augment:
+        u = torch.rand(B, 6, generator=g)
+        draws["aug_search"] = {"trans": u[:, :3] * 0.6 - 0.3, "rot": u[:, 3] * 20 - 10, "flip_x": u[:, 4] < 0.5, "flip_y": u[:, 5] < 0.5}
     batch, valid = siamese_batch(data, cfg, frame_ids, cand, draws=draws, generator=g)
     assert bool(valid.all())
     deg = 5.0 if cfg.degrees else np.deg2rad(5.0)
@@ -45,7 +48,10 @@ def test_batch_matches_reference_restatement(cfg_name):
         off_s = draws["search_offset"][b].double().numpy() * np.sqrt([1.0, 1.0, deg])     # N(0, diag(1, 1, 5 deg))
         want = R.siamese_processing(fr(first), fr(prev), fr(frames[k]), int(cand[b]), cfg,
                                     draws["template_offset"][b].double().numpy(), off_s,
-                                    limit_rand_t=draws["limit_rand_t"][b].tolist(), limit_rand_s=draws["limit_rand_s"][b].tolist())
+                                    limit_rand_t=draws["limit_rand_t"][b].tolist(), limit_rand_s=draws["limit_rand_s"][b].tolist(),
+                                    aug_search=None if not augment else (draws["aug_search"]["trans"][b].double().numpy(),
+                                                                         float(draws["aug_search"]["rot"][b]), bool(draws["aug_search"]["flip_x"][b]),
+                                                                         bool(draws["aug_search"]["flip_y"][b])))
         assert int(batch["_n_template"][b]) == want["n_template"] and int(batch["_n_search"][b]) == want["n_search"]
         assert np.abs(batch["box_label"][b].numpy() - want["box_label"]).max() < 1e-4
         assert np.abs(batch["bbox_size"][b].numpy() - want["bbox_size"]).max() < 1e-6
@@ -86,7 +92,12 @@ def test_motion_batch_matches_reference_restatement():
     B = 8
     g = torch.Generator().manual_seed(6)
     frame_ids, cand = torch.arange(B), torch.tensor([0, 1, 2, 3, 0, 1, 2, 3])
-    draws = {"offset": torch.rand(B, 3, generator=g) * 0.6 - 0.3, "limit_rand": torch.rand(B, 2, generator=g) * 2 - 1}
+    def aug():
+        u = torch.rand(B, 6, generator=g)
+        return {"trans": u[:, :3] * 0.6 - 0.3, "rot": u[:, 3] * 20 - 10, "flip_x": u[:, 4] < 0.5, "flip_y": u[:, 5] < 0.5}
+    assert cfg.use_augmentation                                    # M2_track_kitti.yaml trains with the augmentation transform
+    draws = {"offset": torch.rand(B, 3, generator=g) * 0.6 - 0.3, "limit_rand": torch.rand(B, 2, generator=g) * 2 - 1,
+             "aug_prev": aug(), "aug_this": aug()}
     batch, valid = motion_batch(data, cfg, frame_ids, cand, draws=draws, generator=g)
     assert bool(valid.all())
     n = cfg.point_sample_size
@@ -97,8 +108,9 @@ def test_motion_batch_matches_reference_restatement():
 
     for b in range(B):
         k = int(frame_ids[b])
+        a = lambda d: (d["trans"][b].double().numpy(), float(d["rot"][b]), bool(d["flip_x"][b]), bool(d["flip_y"][b]))
         want = R.motion_processing(fr(frames[int(data.prev[k])]), fr(frames[k]), int(cand[b]), cfg, draws["offset"][b].double().numpy(),
-                                   limit_rand=draws["limit_rand"][b].tolist())
+                                   limit_rand=draws["limit_rand"][b].tolist(), aug_prev=a(draws["aug_prev"]), aug_this=a(draws["aug_this"]))
         assert (int(batch["_n_prev"][b]), int(batch["_n_this"][b]), int(batch["_n_target"][b])) == (want["n_prev"], want["n_this"], want["n_target"])
         for key in ("box_label", "box_label_prev", "motion_label", "bbox_size"):
             assert np.abs(batch[key][b].numpy() - want[key]).max() < 2e-4, key
@@ -127,3 +139,24 @@ def test_motion_batch_matches_reference_restatement():
     from open3dsot_b200.datasets.synthetic import synthetic_motion_batch
     ref = synthetic_motion_batch(4, cfg.point_sample_size)
     assert {k: (tuple(v.shape), v.dtype) for k, v in out.items()} == {k: (tuple(v.shape), v.dtype) for k, v in ref.items()}
+
+
+def test_augmentation_matches_reference_restatement():
+    from open3dsot_b200.datasets.device_sampler import apply_augmentation
+    from open3dsot_b200.tracking import boxes as bx
+    seq = synthetic_sequence(n_frames=4, n_points=3000, seed=51, n_object=500)
+    B = 4
+    pts = torch.stack([torch.tensor(f["pc"].points.T.astype(np.float64)) for f in seq])
+    boxes = bx.Box(*(torch.stack([getattr(f["3d_bbox"].to_tensor(dtype=torch.float64), k) for f in seq]) for k in ("center", "wlh", "rot")))
+    g = torch.Generator().manual_seed(2)
+    trans = torch.rand(B, 3, generator=g, dtype=torch.float64) * 0.6 - 0.3
+    rot = torch.rand(B, generator=g, dtype=torch.float64) * 20 - 10
+    fx, fy = torch.tensor([True, False, True, False]), torch.tensor([True, True, False, False])
+    got_p, got_b = apply_augmentation(pts, boxes, trans, rot, fx, fy)
+    for b in range(B):
+        ob = R.Box(seq[b]["3d_bbox"].center, seq[b]["3d_bbox"].wlh, seq[b]["3d_bbox"].rotation_matrix)
+        want_p, want_b = R.apply_augmentation(seq[b]["pc"].points.astype(np.float64), ob, trans[b].numpy(), float(rot[b]), bool(fx[b]), bool(fy[b]))
+        assert np.abs(got_p[b].numpy().T - want_p).max() < 1e-9
+        assert np.abs(got_b.center[b].numpy() - want_b.center).max() < 1e-9 and np.abs(got_b.rot[b].numpy() - want_b.rot).max() < 1e-9
+        moved = np.abs(want_p - seq[b]["pc"].points).max(0) > 1e-9
+        assert 300 < int(moved.sum()) < 900                         # the object's points moved, the background did not
