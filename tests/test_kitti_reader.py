@@ -90,3 +90,23 @@ def test_reader_feeds_the_device_sampler(tmp_path):
     assert 0 < float(batch["seg_label"].sum()) < 4 * cfg.search_size and torch.isfinite(batch["points2cc_dist_s"]).all()
     seqs = get_dataset(cfg, type="test", split="train_tiny")
     assert [len(s) for s in seqs] == [5, 4] and set(seqs[0][0]) == {"pc", "3d_bbox", "meta"}
+
+
+def test_camera_coordinate_mode(tmp_path):
+    """coordinate_mode='camera' (kitti.py:160-166, :176-177): label kept in the camera frame, scan moved there by Tr_velo_cam."""
+    root = str(tmp_path)
+    seq = synthetic_sequence(n_frames=2, n_points=500, seed=8, n_object=100)
+    _write_scene(root, "0000", [((4, "Car"), seq)])
+    velo = kittiDataset(root, "train_tiny", "Car", coordinate_mode="velodyne").get_frames(0, [1])[0]
+    cam = kittiDataset(root, "train_tiny", "Car", coordinate_mode="camera").get_frames(0, [1])[0]
+    T = np.vstack((TR, [0, 0, 0, 1]))
+    want_pts = (T @ np.vstack((velo["pc"].points, np.ones(velo["pc"].points.shape[1]))))[:3]
+    assert np.abs(cam["pc"].points - want_pts).max() < 1e-5
+    a = cam["meta"]
+    assert np.allclose(cam["3d_bbox"].center, [a["x"], a["y"] - a["height"] / 2, a["z"]])
+    # the same physical box: camera-frame centre = Tr_velo_cam applied to the velodyne-frame centre
+    assert np.abs((T @ np.append(velo["3d_bbox"].center, 1.0))[:3] - cam["3d_bbox"].center).max() < 1e-4
+    r = cam["3d_bbox"].rotation_matrix
+    assert np.abs(r @ r.T - np.eye(3)).max() < 1e-12 and abs(np.linalg.det(r) - 1) < 1e-12
+    # its length axis (box x) in the camera frame is the velodyne heading rotated by Tr_velo_cam
+    assert np.abs(TR[:, :3] @ velo["3d_bbox"].rotation_matrix[:, 0] - r[:, 0]).max() < 1e-5
