@@ -271,3 +271,18 @@ def test_points_utils_names_match_the_restatement():
     p, i = PU.regularize_pc(pts.T, 128, seed=1)
     wp, wi = R.regularize_pc(pts.T, 128, seed=1)
     assert np.array_equal(i, wi) and np.array_equal(p, wp)
+
+
+def test_evaluate_accumulates_success_and_precision():
+    from open3dsot_b200.tracking.evaluate import evaluate
+    seqs = [synthetic_sequence(n_frames=4, n_points=4000, seed=60 + i) for i in range(2)]
+    m = _Echo(_cfg())
+    out = evaluate(m, seqs)
+    ious, dists = [], []
+    for s in seqs:
+        i, d, _ = m.evaluate_one_sequence(s)
+        ious += i
+        dists += d
+    assert out["frames"] == 8 and len(out["results"]) == 2
+    assert abs(out["success"] - R.success(ious)) < 1e-9 and abs(out["precision"] - R.precision(dists)) < 1e-9
+    assert 30 < out["success"] <= 100 and 30 < out["precision"] <= 100
