@@ -359,13 +359,13 @@ def gather_roofline(dev, batch_pairs):
             "algorithmic_bytes_per_launch": alg_bytes}
 
 
-def ncu_traffic(P):
-    """DRAM bytes per launch of the roofline kernel as ncu measured them (dram__bytes_read.sum + dram__bytes_write.sum of
+def ncu_traffic(P, key="fwd"):
+    """DRAM bytes per launch of a roofline kernel as ncu measured them (dram__bytes_read.sum + dram__bytes_write.sum of
     one `--set full` capture of the same kernel and shape, committed under profiles/); None when the shape differs."""
     path = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
     try:
         with open(path) as f:
-            rec = json.load(f)
+            rec = json.load(f)[key]
         return float(rec["dram_bytes_per_launch"]) if f"P={P}," in rec["shape"] else None
     except (OSError, ValueError, KeyError):
         return None
@@ -455,8 +455,8 @@ def roofline_backward_probe(dev, batch_pairs):
                    "o3d_pw_wgrad_tc")
     peaks, how = measured_peaks()
     res = []
-    for name, fn, nbytes in (("pw_tc_kernel<1,TcDy,TcDgradEpi<128>> (dgrad)", dgrad, 4.0 * P * C * 4),
-                             ("pw_wgrad_tc_kernel (wgrad)", wgrad, 4.0 * P * C * 3)):
+    for name, fn, nbytes, key in (("pw_tc_kernel<1,TcDy,TcDgradEpi<128>> (dgrad)", dgrad, 4.0 * P * C * 4, "dgrad"),
+                                  ("pw_wgrad_tc_kernel (wgrad)", wgrad, 4.0 * P * C * 3, "wgrad")):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -470,7 +470,7 @@ def roofline_backward_probe(dev, batch_pairs):
         ms = e0.elapsed_time(e1) / n
         gbs = nbytes / (ms * 1e-3) / 1e9
         res.append({"kernel": name + ", SA2-search layer: P=%d, 128 -> 128 channels" % P, "bound": "hbm", "achieved": gbs,
-                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": ncu_traffic(P, key),
                     "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
                     "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"})
     return res
