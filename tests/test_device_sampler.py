@@ -160,3 +160,20 @@ def test_augmentation_matches_reference_restatement():
         assert np.abs(got_b.center[b].numpy() - want_b.center).max() < 1e-9 and np.abs(got_b.rot[b].numpy() - want_b.rot).max() < 1e-9
         moved = np.abs(want_p - seq[b]["pc"].points).max(0) > 1e-9
         assert 300 < int(moved.sum()) < 900                         # the object's points moved, the background did not
+
+
+def test_ragged_scans_and_single_candidate():
+    """Scans of different lengths are padded (padding rows never survive a crop); num_candidates = 1 always offsets the
+    search box (sampler.py:50-53)."""
+    cfg = load_config(os.path.join(ROOT, "cfgs", "BAT_Car.yaml"), {"num_candidates": 1})
+    tracklets = [synthetic_sequence(n_frames=3, n_points=n, seed=70 + i, n_object=300) for i, n in enumerate((2000, 3500))]
+    data = DeviceTracklets(tracklets, "cpu")
+    assert data.scans.shape == (6, 3500, 3) and data.count.tolist() == [2000] * 3 + [3500] * 3
+    g = torch.Generator().manual_seed(0)
+    frame_ids, cand = torch.arange(6), torch.zeros(6, dtype=torch.long)
+    batch, valid = siamese_batch(data, cfg, frame_ids, cand, generator=g)
+    assert bool(valid.all())
+    assert float(batch["box_label"][:, 3].abs().max()) > 0            # candidate 0 of a 1-candidate sampler is still offset
+    # no padded (all-zero) row of the short scans made it into a search cloud: the origin lies outside every sub-window here
+    assert float(batch["search_points"][:3].abs().sum(-1).min()) > 0
+    assert int(batch["_n_search"][:3].max()) <= 2000 and int(batch["_n_template"][:3].max()) <= 4000   # survivors come from real rows only
