@@ -626,6 +626,18 @@ __global__ void __launch_bounds__(256, 2)
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4 * NQ; ++j) acc[i][j] = 0.f;
+    // per-thread constants: the BN-backward coefficients of this thread's 4 channels and the input prologue of the few
+    // columns (left inside finish_*() the compiler re-loads them for every position)
+    const bool on = m < M;
+    float4 ca = make_float4(1.f, 1.f, 1.f, 1.f), cb = make_float4(0.f, 0.f, 0.f, 0.f), ccf = cb;
+    if (on && din.a) { ca = ld4(din.a + m); cb = ld4(din.b + m); ccf = ld4(din.cc + m); }
+    float4 xs[NQ], xt[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        xs[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+        xt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ain.scale && q * 4 < N) { xs[q] = ld4(ain.scale + q * 4); xt[q] = ld4(ain.shift + q * 4); }
+    }
     for (int p = pbeg + r; p < pend; p += U * R) {
         DyRaw d[U];
         ActRaw x[U][NQ];
@@ -637,11 +649,23 @@ __global__ void __launch_bounds__(256, 2)
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float4 v = finish_dy(din, d[u], p + u * R, pend, m, M);   // zero outside the slice / channel range
+            if (!(on && p + u * R < pend)) continue;          // outside the slice / channel range: contributes nothing
+            float4 v = d[u].g;
+            if (din.a) {
+                const float4 yy = d[u].y;
+                v.x = fmaf(ca.x, v.x, fmaf(ccf.x, yy.x, cb.x)); v.y = fmaf(ca.y, v.y, fmaf(ccf.y, yy.y, cb.y));
+                v.z = fmaf(ca.z, v.z, fmaf(ccf.z, yy.z, cb.z)); v.w = fmaf(ca.w, v.w, fmaf(ccf.w, yy.w, cb.w));
+            }
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                const float4 xv = finish_act(ain, x[u][q], p + u * R, pend, q * 4, N);
+                if (q * 4 >= N) continue;
+                float4 xv = x[u][q].v;
+                if (ain.scale) {
+                    xv.x = fmaf(xv.x, xs[q].x, xt[q].x); xv.y = fmaf(xv.y, xs[q].y, xt[q].y);
+                    xv.z = fmaf(xv.z, xs[q].z, xt[q].z); xv.w = fmaf(xv.w, xs[q].w, xt[q].w);
+                }
+                if (ain.relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f); }
                 const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
