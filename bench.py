@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--track-points", type=int, default=60000, help="points per synthetic scan in --track mode")
     ap.add_argument("--kernel-table", default=None, metavar="FILE",
                     help="also write the per-kernel device times of 3 steps (CUPTI, no replay, warm caches) to FILE")
+    ap.add_argument("--ncu-step", action="store_true", help="run ONE eager step between cudaProfilerStart/Stop and exit (for "
+                    "`ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum`: DRAM bytes per step)")
     ap.add_argument("--cfg", default=None, help="other config to exercise (P2B_Car.yaml, M2_track_kitti.yaml, ...): a parity / "
                     "plumbing run of BASELINE.json configs[2..4], NOT the headline metric")
     return ap.parse_args()
@@ -554,6 +556,14 @@ def run_ours(args):
     for i in range(max(args.warmup, 3) + 3):                    # includes graph capture when enabled
         eng.step(resident[i % n_batches])
     barrier()
+    if args.ncu_step:
+        flush.fill_(1.0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        eng.step(resident[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     # ---- device-resident timing
     sampler = ClockSampler(local)

@@ -3,8 +3,11 @@ legacy non-zip torch format) without pytorch_lightning / easydict installed.
 
 Such a file pickles, besides tensors, an `easydict.EasyDict` (hyper_parameters.config) and a
 `pytorch_lightning.callbacks.model_checkpoint.ModelCheckpoint` class used as a dict key.
-`load_lightning_checkpoint` unpickles with a restricted `find_class`: torch / collections / numpy names resolve normally,
-`easydict.EasyDict` maps to our stand-in, every other foreign global becomes an inert placeholder class.  The result has
+`load_lightning_checkpoint` unpickles with a restricted `find_class`: only an explicit whitelist of (module, name)
+pairs resolves to the real object — the tensor / storage rebuild helpers, `collections.OrderedDict`, the numpy array /
+scalar reconstruction helpers and a few inert builtins containers; `easydict.EasyDict` maps to our stand-in; EVERY other
+global (including `builtins.eval/exec/getattr/__import__`, `os.*`, `torch.hub.*`, `numpy.testing.*`) becomes an inert
+placeholder class whose construction and `__setstate__` do nothing, so a crafted file cannot call into them.  The result has
 the reference's keys: `state_dict`, `hyper_parameters`, `epoch`, `global_step`, `optimizer_states`, …
 """
 import pickle
@@ -13,7 +16,22 @@ import torch
 
 from .compat.easydict import EasyDict
 
-_SAFE_PREFIXES = ("torch", "collections", "numpy", "builtins", "_codecs", "copyreg")
+_STORAGES = {n for n in ("DoubleStorage", "FloatStorage", "HalfStorage", "BFloat16Storage", "LongStorage", "IntStorage",
+                        "ShortStorage", "CharStorage", "ByteStorage", "BoolStorage", "UntypedStorage")}
+# exact (module, name) pairs that resolve to the real object; nothing else does
+_SAFE = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+    ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+    ("torch.serialization", "_get_layout"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "scalar"),
+    ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("_codecs", "encode"),
+    ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "slice"), ("builtins", "complex"),
+    ("builtins", "bytearray"), ("builtins", "list"), ("builtins", "dict"), ("builtins", "tuple"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"),
+} | {("torch", n) for n in _STORAGES} | {("torch.storage", "UntypedStorage"), ("torch.storage", "TypedStorage")}
 
 
 def _placeholder(module, name):
@@ -25,7 +43,9 @@ class _RestrictedUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == "easydict" and name == "EasyDict":
             return EasyDict
-        if module.split(".")[0] in _SAFE_PREFIXES:
+        if (module, name) in _SAFE:
+            return super().find_class(module, name)
+        if module == "torch" and name.endswith("dtype"):
             return super().find_class(module, name)
         return _placeholder(module, name)
 

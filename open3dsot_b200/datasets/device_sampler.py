@@ -30,7 +30,10 @@ class DeviceTracklets:
         k = 0
         for t in tracklets:
             for j, f in enumerate(t):
-                pts = torch.as_tensor(f["pc"].points, dtype=torch.float32).t()[:nmax]
+                if f["pc"].points.shape[1] > nmax:
+                    raise ValueError(f"DeviceTracklets: a scan has {f['pc'].points.shape[1]} points > max_points={nmax}; "
+                                     "raise max_points (scans are never truncated silently)")
+                pts = torch.as_tensor(f["pc"].points, dtype=torch.float32).t()
                 self.scans[k + j, : pts.shape[0]] = pts.to(device)
                 self.count[k + j] = pts.shape[0]
                 b = f["3d_bbox"]
@@ -229,12 +232,13 @@ def motion_batch(data: DeviceTracklets, cfg, frame_ids, candidate_ids, draws=Non
 
 class DeviceSiameseSampler:
     """(`DeviceMotionSampler` below is the same class bound to `motion_batch`.)
-    Drop-in source of training batches: `next_batch()` returns the reference's batch dict, on the device.
+    Drop-in source of training batches: `next_batch()` returns `(batch, valid)`: the reference's batch dict on the device
+    and a (B,) bool mask that is all-True unless every sample of the oversampled pool was rejected.
     On CUDA the construction (≈ 340 small launches, host-bound when issued eagerly) is captured once in a CUDA graph;
     every replay draws new frames and offsets (graph-safe philox offsets of the default CUDA generator) into the same
     static output tensors — consume or copy a batch before asking for the next one."""
 
-    def __init__(self, tracklets, cfg, device, oversample=1.25, seed=0, max_points=None, use_graph=True, processing=None):
+    def __init__(self, tracklets, cfg, device, oversample=1.5, seed=0, max_points=None, use_graph=True, processing=None):
         self.processing = processing or siamese_batch           # `motion_batch` for the motion-centric models
         self.data = tracklets if isinstance(tracklets, DeviceTracklets) else DeviceTracklets(tracklets, device, max_points)
         self.cfg = cfg
@@ -254,7 +258,12 @@ class DeviceSiameseSampler:
         index = torch.randint(0, self.data.num_frames * self.num_candidates, (pool,), device=dev, generator=self.gen)
         batch, valid = self.processing(self.data, self.cfg, index // self.num_candidates, index % self.num_candidates,
                                        generator=self.gen)
-        order = torch.argsort((~valid).to(torch.int8), stable=True)[:B]       # valid samples first, original order kept
+        order = torch.argsort((~valid).to(torch.int8), stable=True)           # valid samples first, original order kept
+        # the reference redraws until a sample is valid (sampler.py:230-242); here the pool is oversampled and, should it
+        # still hold fewer than B valid samples, the valid ones are re-used cyclically (fixed shapes, graph-safe) — a
+        # rejected sample is never handed to the training step unless the whole pool was rejected
+        nvalid = valid.sum().clamp(min=1)
+        order = order[torch.arange(B, device=dev) % nvalid]
         return {k: v[order] for k, v in batch.items() if not k.startswith("_")}, valid[order]
 
     def next_batch(self, batch_size=None):

@@ -105,8 +105,10 @@ class MatchingBaseModel(BaseModel):
         dist = torch.sqrt(torch.sum((proposal_center - box_label[:, None, :3]) ** 2, dim=-1) + 1e-6)
         objectness_label = (dist < 0.3).float()
         objectness_mask = ((dist < 0.3) | (dist > 0.6)).float()
+        # the reference calls BCE with its default MEAN reduction (base_model.py:151-152): the scalar mean over all
+        # proposals is what gets multiplied by the mask — kept exactly (mask only enters through sum/(sum + 1e-6))
         loss_objective = F.binary_cross_entropy_with_logits(
-            estimation_boxes[:, :, 4], objectness_label, reduction='none',
+            estimation_boxes[:, :, 4], objectness_label,
             pos_weight=torch.full((1,), 2.0, device=estimation_boxes.device))   # device-side fill: graph-capturable
         loss_objective = torch.sum(loss_objective * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
 

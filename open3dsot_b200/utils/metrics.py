@@ -3,6 +3,8 @@ or 3-D IoU of two boxes), `estimateAccuracy` (centre distance), and the Success 
 shapely / torchmetrics are replaced by a half-plane clip of the two convex footprints and plain accumulators."""
 import numpy as np
 
+_trapz = getattr(np, "trapezoid", None) or np.trapz   # numpy >= 2.0 renamed trapz
+
 
 def estimateAccuracy(box_a, box_b, dim=3, up_axis=(0, -1, 0)):
     if dim == 3:
@@ -84,7 +86,7 @@ class Success(_Curve):
         if not self.vals:
             return 0.0
         v = np.asarray(self.vals)
-        return float(np.trapezoid([(v >= t).mean() for t in self.xs], self.xs) * 100 / self.top)
+        return float(_trapz([(v >= t).mean() for t in self.xs], self.xs) * 100 / self.top)
 
 
 class Precision(_Curve):
@@ -97,4 +99,4 @@ class Precision(_Curve):
         if not self.vals:
             return 0.0
         v = np.asarray(self.vals)
-        return float(np.trapezoid([(v <= t).mean() for t in self.xs], self.xs) * 100 / self.top)
+        return float(_trapz([(v <= t).mean() for t in self.xs], self.xs) * 100 / self.top)

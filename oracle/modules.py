@@ -237,8 +237,8 @@ def matching_loss(data, output):
     dist = torch.sqrt(torch.sum((centers - box_label[:, None, :3]) ** 2, dim=-1) + 1e-6)
     obj_label = (dist < 0.3).float()
     obj_mask = ((dist < 0.3) | (dist > 0.6)).float()
-    loss_obj = F.binary_cross_entropy_with_logits(boxes[:, :, 4], obj_label, pos_weight=torch.tensor([2.0]),
-                                                  reduction="none")
+    # default MEAN reduction, as the reference calls it (base_model.py:151): the mask multiplies the scalar mean
+    loss_obj = F.binary_cross_entropy_with_logits(boxes[:, :, 4], obj_label, pos_weight=torch.tensor([2.0]))
     loss_obj = torch.sum(loss_obj * obj_mask) / (torch.sum(obj_mask) + 1e-6)
     loss_box = F.smooth_l1_loss(boxes[:, :, :4], box_label[:, None, :4].expand_as(boxes[:, :, :4]), reduction="none")
     loss_box = torch.sum(loss_box.mean(2) * obj_label) / (obj_label.sum() + 1e-6)

@@ -158,10 +158,34 @@ def gen_model(name, cfg_file, B, M, N, out, seed):
     net.train()
     net.log = lambda *a, **k: None
     batch = synthetic_siamese_batch(B, M, N, seed=1234 + seed, box_aware=(name == "bat"))
+    # Place the regression target so that the objectness terms are exercised (base_model.py:142-157): per sample one
+    # proposal centre closer than 0.3 m (label 1, feeds loss_box) and one in the 0.3-0.6 m band (masked out); with the
+    # synthetic labels every centre is farther than 0.6 m and neither term would be pinned.
+    with torch.no_grad():
+        cen = net({k: v.clone() for k, v in batch.items()})["center_xyz"]
+    net.load_state_dict(det_state_dict(net.state_dict(), seed=seed), strict=False)
+    for b in range(B):
+        d = torch.cdist(cen[b], cen[b])
+        ok = ((d > 0.56) & (d < 0.84)).nonzero()
+        assert len(ok), "no pair of proposal centres 0.56-0.84 m apart"
+        i, j = (int(v) for v in ok[0])
+        batch["box_label"][b, :3] = cen[b, i] + 0.25 * (cen[b, j] - cen[b, i]) / d[i, j]
+    out[f"{name}_box_label"] = np_(batch["box_label"])
+    terms = {}
+    ref_compute_loss = net.compute_loss
+
+    def spy(data, output):
+        ld = ref_compute_loss(data, output)
+        terms.update({k: v.detach().clone() for k, v in ld.items()})
+        return ld
+    net.compute_loss = spy
     b2 = {k: v.clone() for k, v in batch.items()}
     loss = net.training_step(b2, 0)
     loss.backward()
+    net.compute_loss = ref_compute_loss
     out[f"{name}_loss"] = np_(loss)
+    for k, v in terms.items():
+        out[f"{name}_term::{k}"] = np_(v)
     sd = dict(net.named_parameters())
     for k in ("conv_final.bias", "backbone.SA_modules.0.mlps.0.layer0.conv.weight",
               "backbone.SA_modules.2.mlps.0.layer2.bn.bn.weight", "rpn.vote_layer.2.conv.bias",
@@ -222,7 +246,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_modules.npz"), **mods)
     models = {}
     gen_model("bat", "BAT_Car.yaml", 2, 256, 512, models, seed=21)
-    gen_model("p2b", "P2B_Car.yaml", 1, 256, 512, models, seed=22)   # BASELINE.json configs[0]
+    gen_model("p2b", "P2B_Car.yaml", 2, 256, 512, models, seed=22)   # BASELINE.json configs[0] shape; B=2 (B=1 is a degenerate BatchNorm case)
     gen_m2track(models)
     np.savez_compressed(os.path.join(HERE, "ref_models.npz"), **models)
     for f in ("ref_modules.npz", "ref_models.npz"):

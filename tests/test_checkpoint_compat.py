@@ -40,3 +40,28 @@ def test_checkpoint_hparams_are_attribute_accessible():
     hp = ck["hyper_parameters"]
     cfg = hp["config"] if "config" in hp else hp
     assert cfg.net_model == "BAT" and cfg.use_fps is True
+
+
+def test_restricted_unpickler_neutralises_foreign_globals(tmp_path):
+    """A crafted pickle that names `builtins.eval` / `os.system` must not reach them: every global outside the exact
+    whitelist resolves to an inert placeholder class (open3dsot_b200/checkpoint.py:_SAFE)."""
+    import io
+    import pickle
+    from open3dsot_b200.checkpoint import _RestrictedUnpickler
+    marker = tmp_path / "pwned"
+    for payload in (b"cbuiltins\neval\n(S'__import__(\"os\").system(\"touch %b\")'\ntR." % str(marker).encode(),
+                    b"cos\nsystem\n(S'touch %b'\ntR." % str(marker).encode(),
+                    b"cbuiltins\ngetattr\n(cbuiltins\n__import__\nS'os'\ntR."):
+        try:
+            _RestrictedUnpickler(io.BytesIO(payload)).load()
+        except Exception:
+            pass                       # an inert placeholder may refuse the call signature; what matters: nothing ran
+    assert not marker.exists()
+    for mod, name in (("builtins", "eval"), ("builtins", "exec"), ("builtins", "getattr"), ("builtins", "__import__"),
+                      ("torch.hub", "load"), ("numpy.testing._private.utils", "runstring"), ("os", "system")):
+        cls = _RestrictedUnpickler(io.BytesIO(b"")).find_class(mod, name)
+        assert isinstance(cls, type) and cls.__module__ == mod and cls("x") is not None
+        import builtins
+        assert cls is not getattr(builtins, name, None)
+    assert _RestrictedUnpickler(io.BytesIO(b"")).find_class("collections", "OrderedDict").__name__ == "OrderedDict"
+    pickle.dumps(1)

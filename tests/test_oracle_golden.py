@@ -99,12 +99,13 @@ def test_xcorr_and_rpn(gm):
     assert rel(vxyz, gm["rpn_vote_xyz"]) < RTOL and rel(cen, gm["rpn_centers"]) < RTOL
 
 
-@pytest.mark.parametrize("name,cfg_file,B,seed", [("bat", "BAT_Car.yaml", 2, 21), ("p2b", "P2B_Car.yaml", 1, 22)])
+@pytest.mark.parametrize("name,cfg_file,B,seed", [("bat", "BAT_Car.yaml", 2, 21), ("p2b", "P2B_Car.yaml", 2, 22)])
 def test_whole_model_forward_loss_grads(gmod, name, cfg_file, B, seed):
     cfg = load_config(os.path.join(ROOT, "cfgs", cfg_file))
     net = get_model(cfg.net_model)(cfg)           # only used for the state-dict key/shape surface
     base = det_state_dict(net.state_dict(), seed=seed)
     batch = synthetic_siamese_batch(B, 256, 512, seed=1234 + seed, box_aware=(name == "bat"))
+    batch["box_label"] = torch.tensor(gmod[f"{name}_box_label"])     # target placed to exercise the objectness bands
     fwd = om.bat_forward if name == "bat" else om.p2b_forward
     trn = om.bat_training_loss if name == "bat" else om.p2b_training_loss
 
@@ -127,8 +128,17 @@ def test_whole_model_forward_loss_grads(gmod, name, cfg_file, B, seed):
     pnames = [k for k, _ in net.named_parameters()]
     for k in pnames:
         sd[k].requires_grad_(True)
-    loss, _, _ = trn(sd, cfg, {k: v.clone() for k, v in batch.items()})
+    loss, ld, out = trn(sd, cfg, {k: v.clone() for k, v in batch.items()})
     assert rel(loss, gmod[f"{name}_loss"]) < RTOL
+    # every loss term on its own (the fixture's target puts proposals below 0.3 m and inside the 0.3-0.6 m band, so the
+    # objectness mask / label are not trivially all-ones / all-zeros and loss_box is live)
+    dist = (out["center_xyz"] - batch["box_label"][:, None, :3]).norm(dim=-1)
+    assert (dist < 0.3).any() and ((dist > 0.3) & (dist < 0.6)).any()
+    terms = [k.split("::")[1] for k in gmod if k.startswith(f"{name}_term::")]
+    assert {"loss_objective", "loss_box", "loss_seg", "loss_vote"} <= set(terms)
+    for k in terms:
+        assert rel(ld[k], gmod[f"{name}_term::{k}"]) < RTOL, k
+    assert float(gmod[f"{name}_term::loss_box"]) > 0
     loss.backward()
     for key in gmod:
         if key.startswith(f"{name}_grad::"):
