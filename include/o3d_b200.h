@@ -191,6 +191,37 @@ int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy, const floa
  * BN-backward, wgrad, dgrad and un-packing of the gradients are all enqueued by one call.
  * ---------------------------------------------------------------------------------------------- */
 #define O3D_MAX_LAYERS 8
+
+/* "Lifted" first layer.  When the first 1x1 convolution of a stack acts on GROUPED rows — QueryAndGroup
+ * (pointnet2_utils.py:317-329: [xyz(idx) - centre, features(idx)]), BoxAwareXCorr's top-k grouping (xcorr.py:87-90) or
+ * P2B_XCorr's [similarity, template xyz, template feature] fusion tensor (xcorr.py:39-46) — its linearity lets the
+ * convolution run ONCE per source point instead of once per (centre, neighbour) position:
+ *     Y0[p, c] = Z[row(p), c] - cc[p / grp, c] + s[p] * u[c]
+ *       Z  = W0 . source rows           (zrows x C0, computed by an ordinary one-layer stack over the source points)
+ *       cc = W0_xyz . centre            (SA layers; NULL otherwise)
+ *       s  = per-position scalar, u = its weight column (P2B's similarity channel; NULL otherwise)
+ * Neither the grouped tensor nor Y0 is written to memory: Y0 exists only inside the operand loaders / epilogues of
+ * the next layer's GEMMs (tensor-core path), its batch statistics come from one gather pass, and the backward is a
+ * scatter of dY0 into dZ / dcc / ds / du.  Layer 0 of the descriptor then carries only BatchNorm / ReLU (weight NULL).
+ * row(p) = cloud(p) * rows_per_cloud + (ridx ? ridx[p] : p % ridx_mod),  cloud(p) = p / pos_per_cloud.             */
+typedef struct o3d_lift_t {
+    const float* z;        /* [zrows, ldz], ldz == round4(C0)                                         */
+    int ldz;
+    const int32_t* ridx;   /* [P] source row of each position, local to its cloud, or NULL            */
+    int ridx_mod;          /* used when ridx == NULL                                                  */
+    int rows_per_cloud;    /* Z rows per cloud                                                        */
+    int pos_per_cloud;     /* positions per cloud                                                     */
+    const float* cc;       /* [P / grp, ldz] or NULL                                                  */
+    int grp;               /* positions per cc row (power of two); also the scatter kernel's work unit */
+    const float* s;        /* [P] or NULL                                                             */
+    const float* u;        /* [ldz] or NULL                                                           */
+    /* backward outputs (NULL = not wanted); d_z, d_s, d_u must be zero-filled by the caller          */
+    float* d_z;            /* [zrows, ldz]   += scatter of dY0                                        */
+    float* d_cc;           /* [P / grp, ldz]  = -sum over the group of dY0                            */
+    float* d_s;            /* [P]            += dY0 . u                                               */
+    float* d_u;            /* [ldz]          += sum_p s[p] * dY0[p]                                   */
+} o3d_lift_t;
+
 typedef struct o3d_stack_t {
     int n_layers;   /* 1..O3D_MAX_LAYERS */
     int P;          /* positions (rows of the channels-last input)                               */
@@ -215,6 +246,7 @@ typedef struct o3d_stack_t {
     float* d_bias[O3D_MAX_LAYERS];
     float* d_gamma[O3D_MAX_LAYERS];
     float* d_beta[O3D_MAX_LAYERS];
+    const o3d_lift_t* lift;   /* non-NULL: layer 0 is lifted (weight[0] == NULL, cout[0] = C0, K0 = round4(C0), x unused) */
 } o3d_stack_t;
 
 long long o3d_stack_workspace_bytes(const o3d_stack_t* d, int backward);

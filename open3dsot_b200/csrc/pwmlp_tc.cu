@@ -26,6 +26,7 @@
 // Shared memory: MT = 1: 3 stages x (W 32K | X 32K) = 192 KB;  MT = 2: 2 stages x (W 64K | X 32K) = 192 KB; K-major
 // SWIZZLE_128B tiles.  The wgrad kernels further down have their own role tables.
 #include "common.cuh"
+#include "lift.cuh"
 #include "../../include/o3d_b200.h"
 
 namespace {
@@ -158,6 +159,79 @@ struct TcAct {
     }
 };
 
+// Lifted first layer as an operand (include/o3d_b200.h: o3d_lift_t): row p of the "activation matrix" is
+//     relu(bn(Y0[p])),  Y0[p, k] = Z[gidx[p], k] - cc[p >> gsh, k] + s[p] * u[k]
+// gathered from the (L2-resident) source-point matrix Z — the grouped tensor and Y0 itself are never stored.
+// Same interface as TcAct; loads stay "raw-first": gidx -> Z row (two dependent loads, the index re-reads hit L1 from the
+// second k-block of a tile on), the subtraction / BN / ReLU happen in finish().
+struct TcLift {
+    static constexpr int DEPTH = 1;
+    LiftView lv; const float* scale; const float* shift; int relu;
+    struct Coef { float4 s, t, u; bool on; };
+    template <int R> struct Batch { float4 v[R]; float4 cv[R]; float sv[R]; bool shared; };
+    __device__ __forceinline__ Coef prep(int k, int K) const {
+        Coef c;
+        c.on = k < K;
+        c.s = make_float4(1.f, 1.f, 1.f, 1.f);
+        c.t = c.u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c.on && scale) { c.s = ld4g(scale + k); c.t = ld4g(shift + k); }
+        if (c.on && lv.u) c.u = ld4g(lv.u + k);
+        return c;
+    }
+    template <int R>
+    __device__ __forceinline__ void fetch(Batch<R>& b, int p0, int stride, int P, int k, int K) const {
+        const int kk = k < K ? k : 0;
+        int row[R];
+        if (R == 4 && stride == 1 && (p0 & 3) == 0 && p0 + 3 < P) {
+            const int4 r4 = __ldg(reinterpret_cast<const int4*>(lv.gidx + p0));
+            row[0] = r4.x; row[R > 1 ? 1 : 0] = r4.y; row[R > 2 ? 2 : 0] = r4.z; row[R > 3 ? 3 : 0] = r4.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int p = p0 + i * stride;
+                row[i] = __ldg(lv.gidx + (p < P ? p : P - 1));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) b.v[i] = ld4g(lv.z + (size_t)row[i] * lv.ldz + kk);
+        b.shared = false;
+        if (lv.cc) {
+            const int pf = p0 < P ? p0 : P - 1;
+            const int pe = p0 + (R - 1) * stride;
+            const int pl = pe < P ? pe : P - 1;
+            if ((pf >> lv.gsh) == (pl >> lv.gsh)) {
+                b.shared = true;
+                b.cv[0] = ld4g(lv.cc + (size_t)(pf >> lv.gsh) * lv.ldz + kk);
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const int p = p0 + i * stride;
+                    b.cv[i] = ld4g(lv.cc + (size_t)((p < P ? p : P - 1) >> lv.gsh) * lv.ldz + kk);
+                }
+            }
+        }
+        if (lv.s) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int p = p0 + i * stride;
+                b.sv[i] = __ldg(lv.s + (p < P ? p : P - 1));
+            }
+        }
+    }
+    template <int R>
+    __device__ __forceinline__ float4 finish(const Batch<R>& b, const Coef& c, int i, int p, int P) const {
+        if (!(c.on && p < P)) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 cv = lv.cc ? (b.shared ? b.cv[0] : b.cv[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = lift_val4(b.v[i], cv, lv.s ? b.sv[i] : 0.f, c.u);
+        if (scale) { v.x = fmaf(v.x, c.s.x, c.t.x); v.y = fmaf(v.y, c.s.y, c.t.y); v.z = fmaf(v.z, c.s.z, c.t.z); v.w = fmaf(v.w, c.s.w, c.t.w); }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        return v;
+    }
+    __device__ __forceinline__ void prefetch_rows(int p0, int rows, int P) const {   // the index slice; Z itself lives in L2
+        if (p0 < P) o3d_prefetch_l2(lv.gidx + p0, (size_t)min(rows, P - p0) * sizeof(int32_t));
+    }
+};
+
 struct TcDy {
     static constexpr int DEPTH = 1;   // 32 raw registers per item: no room for a second one under the 96-register cap
     const float* g; int ldg; const float* y; int ldy; const float* a; const float* b; const float* cc;
@@ -266,6 +340,8 @@ struct TcFwdEpi {
         mx = -INFINITY; mn = INFINITY; ax = an = 0;
     }
     __device__ __forceinline__ void prefetch(int, int, int, int) {}
+    __device__ __forceinline__ const int32_t* lift_gidx() const { return nullptr; }
+    __device__ __forceinline__ void set_tile(const int32_t*) {}
     // Fast path = a full group of 16 positions that lies inside one pooling group (S >= 16, the set-abstraction case):
     // no per-element range or group-boundary test, the max / min / first-arg scan is local to the 16 values and is merged
     // into the running (mx, ax, mn, an) of the pooling group with two compares.  Everything else takes the element-wise path.
@@ -343,17 +419,38 @@ template <int LD>
 struct TcDgradEpi {
     float* out; int ldo; const float* yprev; int ldyp; const float* scale; const float* shift; int relu;
     double* s1g; double* s2y;
+    LiftView lv;             // lv.gidx != nullptr: the previous layer's raw output is the lifted Y0 (gathered, never stored)
     float sc, sh; double d1, d2;
     float yv[16];
+    float uch; const int32_t* gs;   // lifted: this thread's u[ch]; the tile's gidx slice staged in shared memory
     __device__ __forceinline__ void begin(int ch, int Nw) {
         d1 = d2 = 0.0;
         sc = (scale && ch < Nw) ? scale[ch] : 1.f;
         sh = (shift && ch < Nw) ? shift[ch] : 0.f;
+        uch = (lv.gidx && lv.u && ch < Nw) ? lv.u[ch] : 0.f;
+        gs = nullptr;
+    }
+    __device__ __forceinline__ const int32_t* lift_gidx() const { return lv.gidx; }
+    __device__ __forceinline__ void set_tile(const int32_t* g) { gs = g; }
+    // lifted yprev: `col` = first column of the group inside the tile (index into the staged gidx slice)
+    __device__ __forceinline__ void prefetch_lift(int ch, int pbase, int col, int P) {
+        const bool one_grp = lv.cc && lv.gsh >= 4;                      // the 16 positions share one cc row
+        const float ccv = one_grp ? __ldg(lv.cc + (size_t)(pbase >> lv.gsh) * lv.ldz + ch) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int pj = min(pbase + j, P - 1);
+            const float z = __ldg(lv.z + (size_t)gs[col + j] * lv.ldz + ch);
+            const float c = lv.cc ? (one_grp ? ccv : __ldg(lv.cc + (size_t)(pj >> lv.gsh) * lv.ldz + ch)) : 0.f;
+            const float sv = lv.s ? __ldg(lv.s + pj) : 0.f;
+            yv[j] = lift_val(z, c, sv, uch);
+        }
     }
     // (an L2 prefetch of these rows one tile ahead was measured: 7-15 % slower, it competes with the loader's own window)
     // issue the previous layer's raw outputs for this column group before waiting on TMEM (independent loads)
     __device__ __forceinline__ void prefetch(int ch, int Nw, int pbase, int P) {
-        if (!yprev || ch >= Nw) return;
+        if (ch >= Nw) return;
+        if (lv.gidx) { prefetch_lift(ch, pbase, pbase & (TC_N - 1), P); return; }
+        if (!yprev) return;
         if (pbase + 16 <= P) {
             const float* yp = yprev + (size_t)pbase * ldyp + ch;
             const size_t st = LD ? (size_t)LD : (size_t)ldyp;
@@ -375,7 +472,7 @@ struct TcDgradEpi {
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            if (yprev) {
+            if (yprev || lv.gidx) {
                 if (relu) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaf(yv[j], sc, sh) > 0.f ? v[j] : 0.f;
@@ -394,7 +491,7 @@ struct TcDgradEpi {
             for (int j = 0; j < 16; ++j) {
                 if (pbase + j >= P) break;
                 float v = __uint_as_float(r[j]);
-                if (yprev) {
+                if (yprev || lv.gidx) {
                     if (relu && !(fmaf(yv[j], sc, sh) > 0.f)) v = 0.f;
                     s2 = fmaf(v, yv[j], s2);
                 }
@@ -422,7 +519,7 @@ struct TcDgradEpi {
 template <int MT> struct TcCfg {
     static constexpr int STAGES = MT == 2 ? 2 : 3;
     static constexpr int STAGE_BYTES_ = (2 * MT + 2) * TILE_BYTES;      // MT x (Whi|Wlo) | Xhi | Xlo
-    static constexpr int SMEM = STAGES * STAGE_BYTES_ + 1024 + 256;
+    static constexpr int SMEM = STAGES * STAGE_BYTES_ + 1024 + 256 + 1024;   // + alignment | barriers | gidx slices (lifted dgrad)
     static constexpr uint32_t TMEM = MT == 2 ? 512 : 256;
 };
 constexpr int TC2_THREADS = 576;   // 18 warps: 0 MMA | 1 weights | 2,3,12-17 producers | 4-11 epilogue
@@ -535,8 +632,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         epi.begin(ch, Nw);
         const int Nw_e = (dbg & 4) ? 0 : Nw;          // dbg: ch >= Nw_e -> the epilogue body is skipped
         int acc = 0, aphase = 0;
+        int32_t* gsm = reinterpret_cast<int32_t*>(smem + C::STAGES * C::STAGE_BYTES_ + 256);   // [2][TC_N]
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
             const int pt0 = tile_of(t) * TC_N;
+            if (const int32_t* gi = epi.lift_gidx()) {
+                // lifted previous layer: stage the tile's 128 row indices once (warps 4-7), all 8 epilogue warps read them;
+                // the named barrier of tile t+1 orders the re-use of the slice by tile t+2
+                if (grp == 0) gsm[acc * TC_N + q * 32 + lane] = __ldg(gi + min(pt0 + q * 32 + lane, P - 1));
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                epi.set_tile(gsm + acc * TC_N);
+            }
             epi.prefetch(ch, Nw_e, pt0 + cg0 * 16, P);
             o3d_mbar_wait(tfull + acc, aphase);
             tc_fence_after();
@@ -716,8 +821,9 @@ __device__ __forceinline__ void paced_prefetch(const LA& da, const LB& xb, int p
     }
 }
 
+template <class XB>
 __global__ void __launch_bounds__(WG_THREADS, 1)
-    pw_wgrad_tc_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ dW, int lddw, int dbg) {
+    pw_wgrad_tc_kernel(TcDy da, XB xb, int P, int M, int N, int chunk, float* __restrict__ dW, int lddw, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
@@ -854,9 +960,9 @@ __device__ __forceinline__ uint32_t sw_mn2(int p_local, int c4) {   // c4 = floa
     return (uint32_t)((cb + 4 * H * (p_local >> 2)) * 512 + j0 * 128 + ((c32 ^ j0) << 5) + (half << 4));
 }
 
-template <int MH, int NH>
+template <int MH, int NH, class XB>
 __global__ void __launch_bounds__(WG2_THREADS, 1)
-    pw_wgrad_tc2_kernel(TcDy da, TcAct xb, int P, int M, int N, int chunk, float* __restrict__ part, int dbg) {
+    pw_wgrad_tc2_kernel(TcDy da, XB xb, int P, int M, int N, int chunk, float* __restrict__ part, int dbg) {
     using C = Wg2Cfg<MH, NH>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -938,9 +1044,9 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
         const int ca4 = pt % CA, pa0 = pt / CA, sa = 512 / CA;          // A: rows pa0 + sa*i
         const int cb4 = pt % CB, pb0 = pt / CB, sbs = 512 / CB;
         const TcDy::Coef cfa = da.prep(m0 + ca4 * 4, M);
-        const TcAct::Coef cfb = xb.prep(n0 + cb4 * 4, N);
+        const typename XB::Coef cfb = xb.prep(n0 + cb4 * 4, N);
         TcDy::Batch<RA> ra = {};
-        TcAct::Batch<RB> rb = {};
+        typename XB::template Batch<RB> rb = {};
         auto fetch = [&](int kb) {
             if (dbg & 2) return;
             da.fetch(ra, kpos(kb) + pa0, sa, pend, m0 + ca4 * 4, M);
@@ -1095,8 +1201,8 @@ int launch_tc(BLoad bl, const uint8_t* wtiles, int P, int K, int Nw, Epi epi, cu
     return O3D_ERR_ARG;
 }
 
-template <int LD, int MTMASK>
-int launch_fwd(const TcAct& bl, const void* wtiles, const float* bias, int P, int K, int Nw, float* y, int ldy, double* sum,
+template <int LD, int MTMASK, class BLoad>
+int launch_fwd(const BLoad& bl, const void* wtiles, const float* bias, int P, int K, int Nw, float* y, int ldy, double* sum,
                double* sumsq, int S, float* ymax, float* ymin, int32_t* arg, int ldp, cudaStream_t st) {
     TcFwdEpi<LD> ep{};
     ep.y = y; ep.ldy = ldy; ep.bias = bias; ep.sum = sum; ep.sumsq = sumsq;
@@ -1108,8 +1214,10 @@ int launch_fwd(const TcAct& bl, const void* wtiles, const float* bias, int P, in
 
 template <int LD, int MTMASK>
 int launch_dgrad(const TcDy& bl, const void* wtiles_t, int P, int Cout, int Cin, float* out, int ldo, const float* yprev,
-                 int ldyp, const float* pscale, const float* pshift, int prelu, double* s1, double* s2y, cudaStream_t st) {
+                 int ldyp, const float* pscale, const float* pshift, int prelu, double* s1, double* s2y, cudaStream_t st,
+                 const LiftView* lv = nullptr) {
     TcDgradEpi<LD> ep{};
+    if (lv) ep.lv = *lv;
     ep.out = out; ep.ldo = ldo; ep.yprev = yprev; ep.ldyp = ldyp; ep.scale = pscale; ep.shift = pshift; ep.relu = prelu;
     ep.s1g = s1; ep.s2y = s2y;
     // GEMM: D[cin, pos] = sum_cout Wt[cin, cout] * dY[pos, cout]  ->  "K" = Cout, "Nw" = Cin
@@ -1181,6 +1289,28 @@ extern "C" int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy,
 #undef O3D_DG_ARGS
 }
 
+namespace {
+template <class XB>
+int launch_wgrad1(const TcDy& da, const XB& xb, int P, int Cout, int Cin, float* dw, int lddw, cudaStream_t st) {
+    auto kern = pw_wgrad_tc_kernel<XB>;
+    O3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "o3d_pw_wgrad_tc");
+    const int mt = (Cout + TC_M - 1) / TC_M, nt = (Cin + TC_N - 1) / TC_N;
+    int splits = o3d_num_sms() / (mt * nt);
+    if (splits < 1) splits = 1;
+    int chunk = (P + splits - 1) / splits;
+    chunk = ((chunk + TC_K - 1) / TC_K) * TC_K;
+    splits = (P + chunk - 1) / chunk;
+    kern<<<dim3(splits, nt, mt), WG_THREADS, WG_SMEM, st>>>(da, xb, P, Cout, Cin, chunk, dw, lddw, g_tc_debug);
+    O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc");
+    return O3D_OK;
+}
+inline TcLift make_tclift(const o3d_lift_t* lf, const int32_t* gidx, const float* scale, const float* shift, int relu) {
+    int gsh = 0;
+    while ((2 << gsh) <= lf->grp) ++gsh;
+    return TcLift{LiftView{lf->z, lf->ldz, gidx, lf->cc, gsh, lf->s, lf->u}, scale, shift, relu};
+}
+}  // namespace
+
 extern "C" int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
                                const float* cc, const float* dpool, const int32_t* sel, int S, int ldp, const float* x,
                                int ldx, const float* in_scale, const float* in_shift, int in_relu, int P, int Cout,
@@ -1191,24 +1321,15 @@ extern "C" int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy,
     if (P == 0) return O3D_OK;
     TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1), g_tc_debug};
     TcAct xb{x, ldx, in_scale, in_shift, in_relu};
-    O3D_CUDA(cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "o3d_pw_wgrad_tc");
-    const int mt = (Cout + TC_M - 1) / TC_M, nt = (Cin + TC_N - 1) / TC_N;
-    int splits = o3d_num_sms() / (mt * nt);
-    if (splits < 1) splits = 1;
-    int chunk = (P + splits - 1) / splits;
-    chunk = ((chunk + TC_K - 1) / TC_K) * TC_K;
-    splits = (P + chunk - 1) / chunk;
-    pw_wgrad_tc_kernel<<<dim3(splits, nt, mt), WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(da, xb, P, Cout, Cin, chunk, dw, lddw, g_tc_debug);
-    O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc");
-    return O3D_OK;
+    return launch_wgrad1(da, xb, P, Cout, Cin, dw, lddw, (cudaStream_t)stream);
 }
 
 namespace {
-template <int MH, int NH>
-int launch_wgrad2(const TcDy& da, const TcAct& xb, int P, int Cout, int Cin, float* dw, int lddw, float* part,
+template <int MH, int NH, class XB>
+int launch_wgrad2(const TcDy& da, const XB& xb, int P, int Cout, int Cin, float* dw, int lddw, float* part,
                   long long part_floats, cudaStream_t st) {
     using C = Wg2Cfg<MH, NH>;
-    auto kern = pw_wgrad_tc2_kernel<MH, NH>;
+    auto kern = pw_wgrad_tc2_kernel<MH, NH, XB>;
     O3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM), "o3d_pw_wgrad_tc2");
     const int mt = (Cout + 128 * MH - 1) / (128 * MH), nt = (Cin + 128 * NH - 1) / (128 * NH);
     const int Mt = mt * 128 * MH, Nt = nt * 128 * NH;
@@ -1227,6 +1348,15 @@ int launch_wgrad2(const TcDy& da, const TcAct& xb, int P, int Cout, int Cin, flo
     O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc2: reduce");
     return O3D_OK;
 }
+template <class XB>
+int dispatch_wgrad2(const TcDy& da, const XB& xb, int P, int Cout, int Cin, float* dw, int lddw, float* part,
+                    long long part_floats, cudaStream_t st) {
+    const bool m2 = Cout > 128, n2 = Cin > 128;
+    if (m2 && n2) return launch_wgrad2<2, 2>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
+    if (m2) return launch_wgrad2<2, 1>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
+    if (n2) return launch_wgrad2<1, 2>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
+    return launch_wgrad2<1, 1>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
+}
 }  // namespace
 
 extern "C" long long o3d_pw_wgrad_tc2_workspace_floats(void) {
@@ -1243,10 +1373,43 @@ extern "C" int o3d_pw_wgrad_tc2(const float* g, int ldg, const float* y, int ldy
     if (P == 0) return O3D_OK;
     TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1), g_tc_debug};
     TcAct xb{x, ldx, in_scale, in_shift, in_relu};
+    return dispatch_wgrad2(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, (cudaStream_t)stream);
+}
+
+// ---- lifted first layer (o3d_lift_t): the next layer's GEMMs read Y0 through TcLift / the lifted dgrad epilogue ----------
+extern "C" int o3d_pw_wgrad_tc_lift(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
+                                    const float* cc, const float* dpool, const int32_t* sel, int S, int ldp,
+                                    const o3d_lift_t* lf, const int32_t* gidx, const float* in_scale, const float* in_shift,
+                                    int in_relu, int P, int Cout, int Cin, float* dw, int lddw, float* part,
+                                    long long part_floats, void* stream) {
+    O3D_REQUIRE((g || dpool) && lf && gidx && dw, O3D_ERR_ARG, "o3d_pw_wgrad_tc_lift: null pointer");
+    O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0 && lf->ldz == Cin && (lddw & 3) == 0, O3D_ERR_ARG,
+                "o3d_pw_wgrad_tc_lift: channel counts / leading dimensions");
+    if (P == 0) return O3D_OK;
+    TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1), g_tc_debug};
+    const TcLift xb = make_tclift(lf, gidx, in_scale, in_shift, in_relu);
+    if (part) return dispatch_wgrad2(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, (cudaStream_t)stream);
+    return launch_wgrad1(da, xb, P, Cout, Cin, dw, lddw, (cudaStream_t)stream);
+}
+
+extern "C" int o3d_pw_fwd_tc_lift(const o3d_lift_t* lf, const int32_t* gidx, const float* in_scale, const float* in_shift,
+                                  int in_relu, const void* wtiles, const float* bias, int P, int K, int N, float* y, int ldy,
+                                  double* sum, double* sumsq, int S, float* ymax, float* ymin, int32_t* arg, int ldp,
+                                  void* stream) {
+    O3D_REQUIRE(lf && gidx && wtiles, O3D_ERR_ARG, "o3d_pw_fwd_tc_lift: null pointer");
+    O3D_REQUIRE(P >= 0 && K >= 32 && N >= 1 && (K & 3) == 0 && lf->ldz == K, O3D_ERR_ARG, "o3d_pw_fwd_tc_lift: bad sizes");
+    O3D_REQUIRE(lf->cc == nullptr || lf->grp >= 4, O3D_ERR_ARG, "o3d_pw_fwd_tc_lift: grp must be >= 4");
+    O3D_REQUIRE(S == 0 || (P % S == 0 && 64 % S == 0 && ymax && ymin && arg), O3D_ERR_ARG,
+                "o3d_pw_fwd_tc_lift: pooling group size must divide 64 and P");
+    if (P == 0) return O3D_OK;
+    const int Nw = (N + 3) & ~3;
+    const TcLift bl = make_tclift(lf, gidx, in_scale, in_shift, in_relu);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool m2 = Cout > 128, n2 = Cin > 128;
-    if (m2 && n2) return launch_wgrad2<2, 2>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
-    if (m2) return launch_wgrad2<2, 1>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
-    if (n2) return launch_wgrad2<1, 2>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
-    return launch_wgrad2<1, 1>(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, st);
+    const bool two = tc_two_tiles(Nw);
+#define O3D_FWD_ARGS bl, wtiles, bias, P, K, Nw, y, ldy, sum, sumsq, S, ymax, ymin, arg, ldp, st
+    if (ldy == 64 && !two) return launch_fwd<64, 1>(O3D_FWD_ARGS);
+    if (ldy == 128 && !two) return launch_fwd<128, 1>(O3D_FWD_ARGS);
+    if (ldy == 256 && two) return launch_fwd<256, 2>(O3D_FWD_ARGS);
+    return launch_fwd<0, 3>(O3D_FWD_ARGS);
+#undef O3D_FWD_ARGS
 }
