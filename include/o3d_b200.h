@@ -258,6 +258,28 @@ int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float*
 int o3d_stack_backward(const o3d_stack_t* d, const float* x, const void* ws_fwd, void* ws_bwd, const float* out,
                        const float* dout, float* dx, void* stream);
 
+/* Lifted first layer (o3d_lift_t), helpers used by o3d_stack_forward/backward.
+ * o3d_lift_stats : gidx[p] = global Z row of position p; sum / sumsq (nullable) += per-channel batch statistics of Y0;
+ *                  y0 (nullable) receives Y0 itself [P, C0] (the CUDA-core fallback reads it as an ordinary activation).
+ * o3d_lift_scatter: dY0 = a*g + b + cc*Y0 (a == NULL: dY0 = g) scattered into lf->d_z / d_cc / d_s / d_u (see o3d_lift_t);
+ *                  y0 NULL = re-gather Y0 from Z.
+ * o3d_pw_*_tc_lift: the tensor-core GEMMs of the layer AFTER the lifted one, reading Y0 through gidx (never stored).
+ *                  wgrad: part != NULL selects the wide-tile split-K kernel (deterministic), NULL the 128x128 RED kernel.   */
+int o3d_lift_stats(const o3d_lift_t* lf, int P, int C0, int32_t* gidx, float* y0, double* sum, double* sumsq, void* stream);
+int o3d_lift_scatter(const o3d_lift_t* lf, int P, int C0, const int32_t* gidx, const float* y0, const float* g, int ldg,
+                     const float* a, const float* b, const float* cc, void* stream);
+int o3d_pw_fwd_tc_lift(const o3d_lift_t* lf, const int32_t* gidx, const float* in_scale, const float* in_shift, int in_relu,
+                       const void* wtiles, const float* bias, int P, int K, int N, float* y, int ldy, double* sum,
+                       double* sumsq, int S, float* ymax, float* ymin, int32_t* arg, int ldp, void* stream);
+int o3d_pw_dgrad_tc_lift(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
+                         const float* dpool, const int32_t* sel, int S, int ldp, const void* wtiles_t, int P, int Cout,
+                         int Cin, float* out, int ldo, const o3d_lift_t* lf, const int32_t* gidx, const float* pscale,
+                         const float* pshift, int prelu, double* s1, double* s2y, void* stream);
+int o3d_pw_wgrad_tc_lift(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
+                         const float* dpool, const int32_t* sel, int S, int ldp, const o3d_lift_t* lf, const int32_t* gidx,
+                         const float* in_scale, const float* in_shift, int in_relu, int P, int Cout, int Cin, float* dw,
+                         int lddw, float* part, long long part_floats, void* stream);
+
 /* wgrad on the tensor core (MN-major SWIZZLE_128B operands, split over positions, fp32 RED into dw). */
 int o3d_pw_wgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
                     const float* dpool, const int32_t* sel, int S, int ldp, const float* x, int ldx,

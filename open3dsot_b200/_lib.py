@@ -58,6 +58,13 @@ PROTOTYPES = {
                          ctypes.c_longlong, _p],
     "o3d_adam_step": [_p, _p, _p, _p, ctypes.c_longlong, _p, _f, _f, _f, _f, _p],
     "o3d_crop_box_frame": [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p],
+    "o3d_lift_stats": [_p, _i, _i, _p, _p, _p, _p, _p],
+    "o3d_lift_scatter": [_p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p],
+    "o3d_pw_fwd_tc_lift": [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p],
+    "o3d_pw_dgrad_tc_lift": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p,
+                             _p, _p],
+    "o3d_pw_wgrad_tc_lift": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p,
+                             ctypes.c_longlong, _p],
     "o3d_stack_workspace_bytes": [_p, _i],
     "o3d_stack_forward": [_p, _p, _p, _p, _i, _p],
     "o3d_stack_backward": [_p, _p, _p, _p, _p, _p, _p, _p],
@@ -70,6 +77,13 @@ MAX_LAYERS = 8
 _I8, _F8, _P8 = ctypes.c_int * MAX_LAYERS, ctypes.c_float * MAX_LAYERS, ctypes.c_void_p * MAX_LAYERS
 
 
+class LiftDesc(ctypes.Structure):
+    """ctypes mirror of `o3d_lift_t` (include/o3d_b200.h, block 4)."""
+    _fields_ = [("z", _p), ("ldz", _i), ("ridx", _p), ("ridx_mod", _i), ("rows_per_cloud", _i), ("pos_per_cloud", _i),
+                ("cc", _p), ("grp", _i), ("s", _p), ("u", _p),
+                ("d_z", _p), ("d_cc", _p), ("d_s", _p), ("d_u", _p)]
+
+
 class StackDesc(ctypes.Structure):
     """ctypes mirror of `o3d_stack_t` (include/o3d_b200.h, block 4)."""
     _fields_ = [("n_layers", _i), ("P", _i), ("K0", _i), ("S", _i), ("training", _i), ("use_tc", _i),
@@ -78,7 +92,8 @@ class StackDesc(ctypes.Structure):
                 ("momentum", _F8), ("eps", _F8),
                 ("weight", _P8), ("bias", _P8), ("gamma", _P8), ("beta", _P8),
                 ("running_mean", _P8), ("running_var", _P8), ("num_batches_tracked", _P8),
-                ("d_weight", _P8), ("d_bias", _P8), ("d_gamma", _P8), ("d_beta", _P8)]
+                ("d_weight", _P8), ("d_bias", _P8), ("d_gamma", _P8), ("d_beta", _P8),
+                ("lift", ctypes.POINTER(LiftDesc))]
 
 _lib = None
 

@@ -1269,11 +1269,11 @@ extern "C" int o3d_pw_fwd_tc(const float* x, int ldx, const float* in_scale, con
 #undef O3D_FWD_ARGS
 }
 
-extern "C" int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
-                               const float* cc, const float* dpool, const int32_t* sel, int S, int ldp,
-                               const void* wtiles_t, int P, int Cout, int Cin, float* out, int ldo, const float* yprev,
-                               int ldyp, const float* pscale, const float* pshift, int prelu, double* s1, double* s2y,
-                               void* stream) {
+namespace {
+int dgrad_tc_impl(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b, const float* cc,
+                  const float* dpool, const int32_t* sel, int S, int ldp, const void* wtiles_t, int P, int Cout, int Cin,
+                  float* out, int ldo, const float* yprev, int ldyp, const float* pscale, const float* pshift, int prelu,
+                  double* s1, double* s2y, void* stream, const LiftView* lv) {
     O3D_REQUIRE((g || dpool) && wtiles_t && out, O3D_ERR_ARG, "o3d_pw_dgrad_tc: null pointer");
     O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0, O3D_ERR_ARG, "o3d_pw_dgrad_tc: channel counts must be multiples of 4");
     if (P == 0) return O3D_OK;
@@ -1281,12 +1281,36 @@ extern "C" int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy,
     cudaStream_t st = (cudaStream_t)stream;
     const bool two = tc_two_tiles(Cin);
     const int ld = (!yprev || ldyp == ldo) ? ldo : 0;   // one compile-time stride serves both out and yprev
-#define O3D_DG_ARGS bl, wtiles_t, P, Cout, Cin, out, ldo, yprev, ldyp, pscale, pshift, prelu, s1, s2y, st
+#define O3D_DG_ARGS bl, wtiles_t, P, Cout, Cin, out, ldo, yprev, ldyp, pscale, pshift, prelu, s1, s2y, st, lv
     if (ld == 64 && !two) return launch_dgrad<64, 1>(O3D_DG_ARGS);
     if (ld == 128 && !two) return launch_dgrad<128, 1>(O3D_DG_ARGS);
     if (ld == 256 && two) return launch_dgrad<256, 2>(O3D_DG_ARGS);
     return launch_dgrad<0, 3>(O3D_DG_ARGS);
 #undef O3D_DG_ARGS
+}
+}  // namespace
+
+extern "C" int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
+                               const float* cc, const float* dpool, const int32_t* sel, int S, int ldp,
+                               const void* wtiles_t, int P, int Cout, int Cin, float* out, int ldo, const float* yprev,
+                               int ldyp, const float* pscale, const float* pshift, int prelu, double* s1, double* s2y,
+                               void* stream) {
+    return dgrad_tc_impl(g, ldg, y, ldy, a, b, cc, dpool, sel, S, ldp, wtiles_t, P, Cout, Cin, out, ldo, yprev, ldyp, pscale,
+                         pshift, prelu, s1, s2y, stream, nullptr);
+}
+
+// dgrad whose input side is a lifted first layer: the ReLU mask and the BatchNorm-backward sums use Y0 gathered from Z
+extern "C" int o3d_pw_dgrad_tc_lift(const float* g, int ldg, const float* y, int ldy, const float* a, const float* b,
+                                    const float* cc, const float* dpool, const int32_t* sel, int S, int ldp,
+                                    const void* wtiles_t, int P, int Cout, int Cin, float* out, int ldo,
+                                    const o3d_lift_t* lf, const int32_t* gidx, const float* pscale, const float* pshift,
+                                    int prelu, double* s1, double* s2y, void* stream) {
+    O3D_REQUIRE(lf && gidx && lf->ldz == Cin, O3D_ERR_ARG, "o3d_pw_dgrad_tc_lift: lift descriptor");
+    int gsh = 0;
+    while ((2 << gsh) <= lf->grp) ++gsh;
+    const LiftView lv{lf->z, lf->ldz, gidx, lf->cc, gsh, lf->s, lf->u};
+    return dgrad_tc_impl(g, ldg, y, ldy, a, b, cc, dpool, sel, S, ldp, wtiles_t, P, Cout, Cin, out, ldo, nullptr, 0, pscale,
+                         pshift, prelu, s1, s2y, stream, &lv);
 }
 
 namespace {

@@ -122,6 +122,8 @@ __global__ void d2f_kernel(const double* __restrict__ src, int n, float* __restr
 // ---- workspace plan -------------------------------------------------------------------------------------------
 struct Plan {
     int n, P, S, rows;
+    bool lift, virt;     // layer 0 lifted (o3d_lift_t); virt: Y0 is never stored (the tensor-core kernels gather it)
+    size_t gidx;         // [P] int32: global Z row of every position (forward workspace)
     int Nw[O3D_MAX_LAYERS], K[O3D_MAX_LAYERS];
     bool tc_f[O3D_MAX_LAYERS], tc_b[O3D_MAX_LAYERS];
     // forward (persisted) offsets
@@ -137,13 +139,22 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     if (d->n_layers < 1 || d->n_layers > O3D_MAX_LAYERS || d->P < 0 || d->K0 < 4 || (d->K0 & 3)) return false;
     p.n = d->n_layers; p.P = d->P; p.S = d->S;
     p.rows = d->S > 0 ? d->P / d->S : d->P;
+    p.lift = d->lift != nullptr;
+    p.virt = false;
+    if (p.lift && (p.n < 2 || d->weight[0] != nullptr || (d->cout[0] & 3) || d->lift->ldz != d->cout[0] || d->bias[0])) return false;
     size_t o = 0;
     for (int l = 0; l < p.n; ++l) {
         p.Nw[l] = r4(d->cout[l]);
-        p.K[l] = l == 0 ? d->K0 : p.Nw[l - 1];
+        p.K[l] = l == 0 ? (p.lift ? 0 : d->K0) : p.Nw[l - 1];
         p.tc_f[l] = (d->use_tc & 1) && (p.Nw[l] % 128 == 0 || p.Nw[l] == 64) && p.K[l] >= 32 && d->P >= 128 &&
                     !(l == d->n_layers - 1 && d->S > 0 && 64 % d->S != 0);
         p.tc_b[l] = (d->use_tc & 1) && p.K[l] >= 64 && p.Nw[l] >= 32 && d->P >= 128;
+    }
+    if (p.lift) {
+        // Y0 stays virtual when all three GEMMs of layer 1 run on the tensor cores over whole 32-channel k-blocks
+        const bool tcw1 = (d->use_tc & 2) && p.Nw[1] >= 64 && p.K[1] >= 64 && d->P >= 4096;
+        p.virt = p.tc_f[1] && p.tc_b[1] && tcw1 && tc_main(p.K[1]) == p.K[1] && p.K[1] % 32 == 0 &&
+                 (d->lift->cc == nullptr || d->lift->grp >= 4) && !(d->use_tc & 8);
     }
     // statistics block first (one memset)
     p.stat_all = o;
@@ -156,8 +167,9 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
         p.bias[l] = o; o += al(sizeof(float) * p.Nw[l]);
         p.tiles[l] = o; if (p.tc_f[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(p.Nw[l], p.K[l]));
         p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(tc_main(p.K[l]), p.Nw[l]));
-        p.y[l] = o; o += al(sizeof(float) * (size_t)p.P * p.Nw[l]);
+        p.y[l] = o; if (!(l == 0 && p.virt)) o += al(sizeof(float) * (size_t)p.P * p.Nw[l]);
     }
+    p.gidx = o; if (p.lift) o += al(sizeof(int32_t) * (size_t)p.P);
     const size_t gsz = al(sizeof(float) * (size_t)p.rows * p.Nw[p.n - 1]);
     p.ymax = o; o += p.S > 0 ? gsz : 0;
     p.ymin = o; o += p.S > 0 ? gsz : 0;
@@ -205,7 +217,7 @@ extern "C" long long o3d_stack_workspace_bytes(const o3d_stack_t* d, int backwar
 
 extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float* out, int keep_for_backward,
                                  void* stream) {
-    O3D_REQUIRE(d && x && ws_fwd && out, O3D_ERR_ARG, "o3d_stack_forward: null pointer");
+    O3D_REQUIRE(d && (x || d->lift) && ws_fwd && out, O3D_ERR_ARG, "o3d_stack_forward: null pointer");
     Plan p;
     O3D_REQUIRE(make_plan(d, p), O3D_ERR_ARG, "o3d_stack_forward: bad stack description");
     O3D_REQUIRE(p.S == 0 || (128 % p.S == 0 && p.P % p.S == 0), O3D_ERR_ARG, "o3d_stack_forward: group size %d", p.S);
@@ -228,6 +240,7 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
             q.cout = d->cout[l]; q.cin = d->cin[l]; q.Nw = Nw; q.K = K; q.xyz_first = l == 0 ? d->xyz_first : 0;
             q.Km = tc_main(K);
             q.Npad = Nw; q.Kpad = K;
+            if (l == 0 && p.lift) { q.Npad = 0; q.bias_p = nullptr; q.tiles_f = q.tiles_b = nullptr; }   // no weight: nothing to pack
             if (q.tiles_f) { q.Npad = ((Nw + 127) / 128) * 128; q.Kpad = ((K + 31) / 32) * 32; }
             if (q.tiles_b) {
                 if (q.Npad < ((Nw + 31) / 32) * 32) q.Npad = ((Nw + 31) / 32) * 32;
@@ -258,7 +271,14 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
         float* ymin = pool ? at<float>(ws, p.ymin) : nullptr;
         int32_t* arg = pool ? at<int32_t>(ws, p.arg) : nullptr;
         int rc;
-        if (p.tc_f[l]) {
+        if (l == 0 && p.lift) {
+            // lifted layer: one gather pass = row indices + batch statistics (+ Y0 itself on the CUDA-core fallback)
+            rc = o3d_lift_stats(d->lift, p.P, Nw, at<int32_t>(ws, p.gidx), p.virt ? nullptr : y, sum, sumsq, stream);
+        } else if (l == 1 && p.virt) {
+            o3d_pw_tc_set_reverse(0);
+            rc = o3d_pw_fwd_tc_lift(d->lift, at<int32_t>(ws, p.gidx), in_scale, in_shift, in_relu, ws + p.tiles[l], bias, p.P, K,
+                                    cout, y, Nw, sum, sumsq, pool ? p.S : 0, ymax, ymin, arg, Nw, stream);
+        } else if (p.tc_f[l]) {
             // snake order: layer 0 starts where the grouping kernel finished (the end), layer 1 where layer 0 finished, ...
             o3d_pw_tc_set_reverse((l & 1) == 0);
             void* tiles = ws + p.tiles[l];
@@ -299,7 +319,7 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
 
 extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const void* ws_fwd, void* ws_bwd, const float* out,
                                   const float* dout, float* dx, void* stream) {
-    O3D_REQUIRE(d && x && ws_fwd && ws_bwd && out && dout, O3D_ERR_ARG, "o3d_stack_backward: null pointer");
+    O3D_REQUIRE(d && (x || d->lift) && ws_fwd && ws_bwd && out && dout, O3D_ERR_ARG, "o3d_stack_backward: null pointer");
     Plan p;
     O3D_REQUIRE(make_plan(d, p), O3D_ERR_ARG, "o3d_stack_backward: bad stack description");
     if (p.P == 0) return O3D_OK;
@@ -346,6 +366,16 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         } else if (d->d_bias[l]) {
             d2f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(s1(l), cout, d->d_bias[l]);
         }
+        if (l == 0 && p.lift) {
+            // the lifted layer has no GEMM: dY0 = a*g + b + cc*Y0 is scattered into dZ / dcc / ds / du
+            const o3d_lift_t* lf = d->lift;
+            if (lf->d_z || lf->d_cc || lf->d_s || lf->d_u) {
+                rc = o3d_lift_scatter(lf, p.P, Nl, at<int32_t>(wf, p.gidx), p.virt ? nullptr : at<float>(wf, p.y[0]), g, Nl, a, b,
+                                      cc, stream);
+                if (rc) return rc;
+            }
+            break;
+        }
         const bool pooled = (l == L && p.S > 0);
         const float* gl = pooled ? nullptr : g;
         const float* yl = a ? at<float>(wf, p.y[l]) : nullptr;
@@ -366,7 +396,11 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
             const float* yprev = mask ? at<float>(wf, p.y[l - 1]) : nullptr;
             double* ps1 = want ? s1(l - 1) : nullptr;
             double* ps2 = want ? s1(l - 1) + K : nullptr;
-            if (p.tc_b[l]) {
+            if (l == 1 && p.virt) {
+                o3d_pw_tc_set_reverse(0);
+                rc = o3d_pw_dgrad_tc_lift(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, wf + p.btiles[l], p.P, Nl, K, gout, K, d->lift,
+                                          at<int32_t>(wf, p.gidx), psc, psh, prelu, ps1, ps2, stream);
+            } else if (p.tc_b[l]) {
                 o3d_pw_tc_set_reverse(0);   // dgrad sweeps forward; the wgrad that follows sweeps the same rows backward
                 // tensor cores on the first floor(K/128)*128 input channels, exact CUDA-core kernel on the ragged tail
                 // (the xyz / box-cloud extras of a first layer)
@@ -392,7 +426,11 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         if (d->d_weight[l]) {
             float* dwp = at<float>(wb, p.dwp[l]);
             const bool tcw = (d->use_tc & 2) && Nl >= 64 && K >= 64 && p.P >= 4096;
-            if (tcw) {
+            if (l == 1 && p.virt) {
+                const bool wide = (d->use_tc & 4) == 0 && Nl % 128 == 0 && K % 128 == 0 && (Nl >= 256 || K >= 256);
+                rc = o3d_pw_wgrad_tc_lift(gl, Nl, yl, Nl, a, b, cc, dpl, sel, Sg, Nl, d->lift, at<int32_t>(wf, p.gidx), psc, psh, prelu,
+                                          p.P, Nl, K, dwp, K, wide ? at<float>(wb, p.wpart) : nullptr, p.wpart_floats, stream);
+            } else if (tcw) {
                 // tensor-core part: the first floor(K/128)*128 input channels; ragged tail (xyz / box-cloud extras)
                 // goes through the exact CUDA-core kernel on the remaining columns
                 const int Kmain = tc_main(K);

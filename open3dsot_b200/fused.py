@@ -35,10 +35,10 @@ def _ptr(t):
 
 # ---------------------------------------------------------------------------------------------- layer parsing
 class _LayerSpec:
-    __slots__ = ("weight", "bias", "bn", "relu")
+    __slots__ = ("weight", "bias", "bn", "relu", "lift_c0")
 
-    def __init__(self, weight, bias, bn, relu):
-        self.weight, self.bias, self.bn, self.relu = weight, bias, bn, relu
+    def __init__(self, weight, bias, bn, relu, lift_c0=0):
+        self.weight, self.bias, self.bn, self.relu, self.lift_c0 = weight, bias, bn, relu, lift_c0
 
 
 def _spec_from_unit(unit):
@@ -89,8 +89,9 @@ class _Meta:
         self.dx_cols = int(dx_cols)
         self.bns = [s.bn for s in specs]
         self.relu = [bool(s.relu) for s in specs]
-        self.cout = [s.weight.shape[0] for s in specs]
-        self.cin = [s.weight.numel() // s.weight.shape[0] for s in specs]
+        # a spec without weight is the lifted first layer (BatchNorm / ReLU only; `lift_c0` output channels)
+        self.cout = [s.weight.shape[0] if s.weight is not None else s.lift_c0 for s in specs]
+        self.cin = [s.weight.numel() // s.weight.shape[0] if s.weight is not None else 0 for s in specs]
 
 
 def _describe(meta, P, K0, params):
@@ -102,7 +103,7 @@ def _describe(meta, P, K0, params):
         W, b, g, be = params[4 * l:4 * l + 4]
         bn = meta.bns[l]
         d.cin[l], d.cout[l], d.relu[l], d.has_bn[l] = meta.cin[l], meta.cout[l], int(meta.relu[l]), int(bn is not None)
-        d.weight[l], d.bias[l], d.gamma[l], d.beta[l] = W.data_ptr(), _ptr(b), _ptr(g), _ptr(be)
+        d.weight[l], d.bias[l], d.gamma[l], d.beta[l] = _ptr(W), _ptr(b), _ptr(g), _ptr(be)
         if bn is not None:
             d.momentum[l] = 0.1 if bn.momentum is None else bn.momentum
             d.eps[l] = bn.eps
@@ -170,6 +171,106 @@ class _MLPStackFn(torch.autograd.Function):
         return (None, dx, *grads)
 
 
+# ---------------------------------------------------------------------------------------------- lifted first layer
+class _LiftGeom:
+    """Static geometry of a lifted stack: Y0[p] = Z[cloud(p) * rows_per_cloud + (ridx[p] | p % ridx_mod)] - cc[p // grp] + s[p] * u."""
+    __slots__ = ("P", "ridx_mod", "rows_per_cloud", "pos_per_cloud", "grp")
+
+    def __init__(self, P, ridx_mod, rows_per_cloud, pos_per_cloud, grp):
+        self.P, self.ridx_mod, self.rows_per_cloud, self.pos_per_cloud, self.grp = P, ridx_mod, rows_per_cloud, pos_per_cloud, grp
+
+
+class _LiftedStackFn(torch.autograd.Function):
+    """A stack whose first 1x1 convolution has been applied to the SOURCE points (z = W0 . rows, an ordinary one-layer
+    stack): include/o3d_b200.h `o3d_lift_t`.  Inputs: z (rows, C0), ridx (P,) int32 | None, cc (P/grp, C0) | None,
+    s (P,) | None, u (C0,) | None; params as in _MLPStackFn with layer 0 = (None, None, gamma0, beta0)."""
+
+    @staticmethod
+    def forward(ctx, meta, geom, z, ridx, cc, s, u, *params):
+        P, C0 = geom.P, z.shape[1]
+        for t in (z, ridx, cc, s, u) + tuple(params):
+            if t is not None and not t.is_contiguous():
+                raise RuntimeError("lifted MLP stack: tensors must be contiguous")
+        d = _describe(meta, P, C0, params)
+        lf = _lib.LiftDesc()
+        lf.z, lf.ldz, lf.ridx, lf.ridx_mod = z.data_ptr(), C0, _ptr(ridx), geom.ridx_mod
+        lf.rows_per_cloud, lf.pos_per_cloud, lf.cc, lf.grp = geom.rows_per_cloud, geom.pos_per_cloud, _ptr(cc), geom.grp
+        lf.s, lf.u = _ptr(s), _ptr(u)
+        d.lift = ctypes.pointer(lf)
+        L = _lib.lib()
+        need_grad = any(ctx.needs_input_grad)
+        nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 0)
+        if nbytes < 0:
+            raise RuntimeError("lifted MLP stack: invalid stack description")
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=z.device)
+        rows = P // meta.S if meta.S > 0 else P
+        Nw, Cout = _r4(meta.cout[-1]), meta.cout[-1]
+        out = torch.empty(rows, Nw, dtype=torch.float32, device=z.device)
+        ops.LAUNCHES += 3 * meta.n + 1
+        _lib.check(L.o3d_stack_forward(ctypes.byref(d), None, ws.data_ptr(), out.data_ptr(), int(need_grad), _stream()),
+                   "o3d_stack_forward (lifted)")
+        if need_grad:
+            ctx.meta, ctx.geom, ctx.desc, ctx.lf, ctx.params = meta, geom, d, lf, params
+            ctx.save_for_backward(z, ridx, cc, s, u, ws, out)
+        return out if Nw == Cout else out[:, :Cout]
+
+    @staticmethod
+    def backward(ctx, dout):
+        meta, geom, d, lf, params = ctx.meta, ctx.geom, ctx.desc, ctx.lf, ctx.params
+        z, ridx, cc, s, u, ws, out = ctx.saved_tensors
+        Nw = out.shape[1]
+        if dout.shape[1] != Nw or not dout.is_contiguous():
+            dpad = torch.zeros(out.shape, dtype=torch.float32, device=z.device)
+            dpad[:, :dout.shape[1]] = dout
+            dout = dpad
+        grads = [None] * (4 * meta.n)
+        fields = (d.d_weight, d.d_bias, d.d_gamma, d.d_beta)
+        for l in range(meta.n):
+            for j in range(4):
+                t = params[4 * l + j]
+                if t is not None and ctx.needs_input_grad[7 + 4 * l + j]:
+                    gt = torch.empty_like(t)
+                    grads[4 * l + j] = gt
+                    fields[j][l] = gt.data_ptr()
+                else:
+                    fields[j][l] = None
+        need = ctx.needs_input_grad
+        dz = torch.zeros_like(z) if need[2] else None
+        dcc = torch.empty_like(cc) if (cc is not None and need[4]) else None
+        ds = torch.zeros_like(s) if (s is not None and need[5]) else None
+        du = torch.zeros_like(u) if (u is not None and need[6]) else None
+        lf.d_z, lf.d_cc, lf.d_s, lf.d_u = _ptr(dz), _ptr(dcc), _ptr(ds), _ptr(du)
+        L = _lib.lib()
+        nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 1)
+        wb = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=z.device)
+        ops.LAUNCHES += 5 * meta.n + 1
+        _lib.check(L.o3d_stack_backward(ctypes.byref(d), None, ws.data_ptr(), wb.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                                        None, _stream()), "o3d_stack_backward (lifted)")
+        return (None, None, dz, None, dcc, ds, du, *grads)
+
+
+def lifted_stack(z, specs, geom, ridx=None, cc=None, s=None, u=None, S=0, training=True):
+    """specs[0] is the lifted layer: its conv has ALREADY been applied (that is `z`); only its BatchNorm / ReLU remain."""
+    first = _LayerSpec(None, None, specs[0].bn, specs[0].relu, lift_c0=z.shape[1])
+    meta = _Meta([first] + list(specs[1:]), S, training)
+    params = [None, None, first.bn.weight if first.bn is not None else None, first.bn.bias if first.bn is not None else None]
+    for sp in specs[1:]:
+        params += [sp.weight, sp.bias, sp.bn.weight if sp.bn is not None else None, sp.bn.bias if sp.bn is not None else None]
+    return _LiftedStackFn.apply(meta, geom, z, ridx, cc, s, u, *params)
+
+
+def _pow2_divisor(n, cap=64):
+    g = 1
+    while g * 2 <= cap and n % (g * 2) == 0:
+        g *= 2
+    return g
+
+
+def _liftable(specs):
+    """The first conv can be lifted when another layer follows it, its output width is a multiple of 4, and lifting is on."""
+    return runtime.lift_enabled() and len(specs) >= 2 and specs[0].weight.shape[0] % 4 == 0
+
+
 def mlp_stack(x2d, specs, S=0, training=True, xyz_first=False, c0=0, dx_cols=0):
     """Run a stack on a channels-last matrix.
 
@@ -234,18 +335,36 @@ def sa_forward(sa, xyz, features, sample_idxs):
         S = grouper.nsample
         if 128 % S != 0:
             raise RuntimeError(f"fused SA layer: nsample={S} must divide 128")
-        grouped, _idx = pointnet2_utils.query_and_group_cl(xyz, new_xyz, feat_cl, grouper.radius, S,
-                                                           grouper.normalize_xyz)
         specs = parse_stack(mlp)
         if not grouper.use_xyz:
             raise RuntimeError("fused SA layer expects use_xyz=True (every shipped model does)")
-        # the reference's channel order is [xyz(3), features(C)]; kernel rows are [features(Cp) | dx dy dz 0]:
-        # the re-ordering of the first conv's columns happens inside o3d_stack_forward (xyz_first)
-        # coordinates that carry no gradient (every backbone layer; not the RPN's votes) spare the backward its
-        # (dx,dy,dz) columns
         need_xyz = torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad)
-        pooled = mlp_stack(grouped.view(B * npoint * S, Cp + 4), specs, S, sa.training, xyz_first=True, c0=C,
-                           dx_cols=0 if (need_xyz or Cp == 0) else Cp)
+        if _liftable(specs) and not grouper.normalize_xyz:
+            # Lifted first layer: W0 . [x(idx) - c, f(idx)] = (W0 . [x, f])[idx] - W0_xyz . c  — the convolution runs once per
+            # SOURCE point (z) and once per centre (cc); the grouped (B, 3+C, npoint, nsample) tensor never exists
+            # (pointnet2_utils.py:317-329 + the first SharedMLP layer, pointnet2_modules.py:64-69).
+            W0 = specs[0].weight
+            C0 = W0.shape[0]
+            if feat_cl is None:
+                rows = F.pad(xyz, (0, 1))                                               # (B, N, 4): [x y z 0]
+            else:
+                rows = torch.cat([feat_cl, xyz, xyz.new_zeros(B, N, 1)], dim=2)         # (B, N, Cp + 4): [features | x y z 0]
+            z = mlp_stack(rows.view(B * N, rows.shape[2]), [_LayerSpec(W0, specs[0].bias, None, False)], 0, sa.training,
+                          xyz_first=True, c0=C, dx_cols=0 if (need_xyz or Cp == 0) else Cp)
+            Wx = W0.reshape(C0, -1)[:, :3].contiguous()
+            cc = mlp_stack(F.pad(new_xyz, (0, 1)).view(B * npoint, 4), [_LayerSpec(Wx, None, None, False)], 0, sa.training)
+            idx = pointnet2_utils.ball_query(grouper.radius, S, xyz, new_xyz)            # (B, npoint, S) int32, non-differentiable
+            geom = _LiftGeom(B * npoint * S, 0, N, npoint * S, S)
+            pooled = lifted_stack(z, specs, geom, ridx=idx.view(-1), cc=cc, S=S, training=sa.training)
+        else:
+            grouped, _idx = pointnet2_utils.query_and_group_cl(xyz, new_xyz, feat_cl, grouper.radius, S,
+                                                               grouper.normalize_xyz)
+            # the reference's channel order is [xyz(3), features(C)]; kernel rows are [features(Cp) | dx dy dz 0]:
+            # the re-ordering of the first conv's columns happens inside o3d_stack_forward (xyz_first)
+            # coordinates that carry no gradient (every backbone layer; not the RPN's votes) spare the backward its
+            # (dx,dy,dz) columns
+            pooled = mlp_stack(grouped.view(B * npoint * S, Cp + 4), specs, S, sa.training, xyz_first=True, c0=C,
+                               dx_cols=0 if (need_xyz or Cp == 0) else Cp)
         outs.append(from_channels_last(pooled.reshape(B, npoint, pooled.shape[1])))
     return new_xyz, outs
 
@@ -317,8 +436,16 @@ def boxaware_xcorr_forward(xc, template_feature, search_feature, template_xyz, t
     C = tmpl.shape[2]
     if C % 4:
         tmpl = F.pad(tmpl, (0, _r4(C) - C))
-    rows = _GroupRowsCL.apply(tmpl.contiguous(), topk.view(B, N * k))                 # (B, N*k, Cp)
-    pooled = mlp_stack(rows.view(B * N * k, rows.shape[2]), parse_stack(xc.mlp), k, xc.training)
+    specs = parse_stack(xc.mlp)
+    if _liftable(specs) and (N * k) % 4 == 0:
+        # lifted: the first conv runs on the M template rows; the (B, 268, N, k) grouped tensor is never built (xcorr.py:89-98)
+        tm = tmpl.contiguous()
+        z = mlp_stack(tm.view(B * M, tm.shape[2]), [_LayerSpec(specs[0].weight, specs[0].bias, None, False)], 0, xc.training)
+        geom = _LiftGeom(B * N * k, 0, M, N * k, _pow2_divisor(N * k))
+        pooled = lifted_stack(z, specs, geom, ridx=topk.view(-1), S=k, training=xc.training)
+    else:
+        rows = _GroupRowsCL.apply(tmpl.contiguous(), topk.view(B, N * k))                 # (B, N*k, Cp)
+        pooled = mlp_stack(rows.view(B * N * k, rows.shape[2]), specs, k, xc.training)
     fusion = from_channels_last(pooled.reshape(B, N, pooled.shape[1]))
     return seq_forward(xc.fea_layer, fusion)
 
@@ -332,13 +459,29 @@ def p2b_xcorr_forward(xc, template_feature, search_feature, template_xyz):
         raise RuntimeError(f"fused P2B_XCorr: number of template points {n1} must divide 128")
     sim = F.cosine_similarity(template_feature.unsqueeze(-1), search_feature.unsqueeze(2), dim=1)   # (B,n1,n2), eps 1e-8
     t_cl = template_feature.transpose(1, 2)                                                        # (B,n1,f)
-    fusion = torch.cat([sim.transpose(1, 2).unsqueeze(-1),                                          # (B,n2,n1,1)
-                        template_xyz.unsqueeze(1).expand(B, n2, n1, 3),
-                        t_cl.unsqueeze(1).expand(B, n2, n1, f)], dim=3)
-    C = fusion.shape[3]
-    if C % 4:
-        fusion = F.pad(fusion, (0, _r4(C) - C))
-    pooled = mlp_stack(fusion.reshape(B * n2 * n1, fusion.shape[3]), parse_stack(xc.mlp), n1, xc.training)
+    specs = parse_stack(xc.mlp)
+    if _liftable(specs) and (n1 & (n1 - 1)) == 0:
+        # lifted: the first conv's input [sim(1), xyz(3), feature(f)] (xcorr.py:39-46) is a per-template row plus ONE scalar
+        # per (search, template) pair, so Y0[(b,j,i)] = (W[:,1:] . [xyz_i, f_i]) + sim[b,i,j] * W[:,0] and the
+        # (B, 260, n1, n2) fusion tensor is never built
+        W0 = specs[0].weight.reshape(specs[0].weight.shape[0], -1)
+        rows = torch.cat([template_xyz, t_cl], dim=2)                                               # (B, n1, 3 + f)
+        C = rows.shape[2]
+        if C % 4:
+            rows = F.pad(rows, (0, _r4(C) - C))
+        z = mlp_stack(rows.reshape(B * n1, rows.shape[2]), [_LayerSpec(W0[:, 1:].contiguous(), specs[0].bias, None, False)], 0,
+                      xc.training)
+        geom = _LiftGeom(B * n2 * n1, n1, n1, n2 * n1, n1)
+        pooled = lifted_stack(z, specs, geom, s=sim.transpose(1, 2).reshape(-1), u=W0[:, 0].contiguous(), S=n1,
+                              training=xc.training)
+    else:
+        fusion = torch.cat([sim.transpose(1, 2).unsqueeze(-1),                                      # (B,n2,n1,1)
+                            template_xyz.unsqueeze(1).expand(B, n2, n1, 3),
+                            t_cl.unsqueeze(1).expand(B, n2, n1, f)], dim=3)
+        C = fusion.shape[3]
+        if C % 4:
+            fusion = F.pad(fusion, (0, _r4(C) - C))
+        pooled = mlp_stack(fusion.reshape(B * n2 * n1, fusion.shape[3]), specs, n1, xc.training)
     out = from_channels_last(pooled.reshape(B, n2, pooled.shape[1]))
     return seq_forward(xc.fea_layer, out)
 

@@ -9,6 +9,20 @@ _FUSED = os.environ.get("O3D_FUSED", "1") != "0"
 _TC = int(os.environ.get("O3D_TC", "3"))
 
 
+# Lifted first layer of grouped stacks (include/o3d_b200.h o3d_lift_t): 1 = the grouped tensor is never built (default),
+# 0 = materialising ball-query+group kernel followed by a GEMM over the grouped rows (round-1 path, kept as a cross-check)
+_LIFT = os.environ.get("O3D_LIFT", "1") != "0"
+
+
+def lift_enabled() -> bool:
+    return _LIFT
+
+
+def set_lift(flag: bool) -> None:
+    global _LIFT
+    _LIFT = bool(flag)
+
+
 def tc_enabled() -> bool:
     return _TC != 0
 
