@@ -4,8 +4,9 @@ Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W`; 
 torchrun, one rank per GPU.  Rank 0 prints ONE JSON line.
 
   value        whole-job pairs/s with the batch already resident in HBM (device-timed, CUDA events, max over ranks)
-  e2e          the same metric through the public API `model.training_step(batch)` fed from PINNED HOST memory:
-               H2D copy of the batch + the step + D2H read of the loss inside the timed region
+  e2e          the same metric through the public engine call `TrainStep.step(batch)` (open3dsot_b200/engine.py: zero-grad,
+               `model.training_step`, backward, gradient all-reduce, Adam) fed from PINNED HOST memory: H2D copy of the batch
+               + the step + D2H read of the loss inside the timed region
   roofline     the dominant kernel timed alone, live, with CUDA events on its launch stream
   cpu_baseline the oracle (CPU restatement of the reference path) on a bounded sample of the same workload
   --impl reference   times only that CPU path (the reference ships no CPU/native code of its own: SURVEY.md facts 1-3)
@@ -517,6 +518,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa_cpus = ddp.pin_to_gpu_numa_node(local) if world > 1 else 0     # ranks stay on the socket next to their GPU
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
@@ -541,8 +543,13 @@ def run_ours(args):
         host = [synthetic_siamese_batch(args.batch, cfg.template_size, cfg.search_size, seed=20260924 + rank * 100 + i,
                                         box_aware=getattr(cfg, "box_aware", False), pin_memory=True)
                 for i in range(n_batches)]
-    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    # every batch is ONE slab (engine.BatchSlab): a step's inputs move with a single copy per hop
+    from open3dsot_b200.engine import BatchSlab
+    host_slabs = [BatchSlab.like(b, "cpu", pin=True).load(b) for b in host]
+    resident = [host_slabs[0].sibling(dev) for _ in host]
+    for r, hs in zip(resident, host_slabs):
+        r.buf.copy_(hs.buf)
+    h2d_bytes = host_slabs[0].nbytes
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def barrier():
@@ -591,7 +598,7 @@ def run_ours(args):
     # the host synchronises once at the end, as a training loop that logs asynchronously does
     barrier()
     copy_stream = torch.cuda.Stream()
-    staging = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    staging = [host_slabs[0].sibling(dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
@@ -605,8 +612,7 @@ def run_ours(args):
         with torch.cuda.stream(copy_stream):
             if i >= 2:
                 copy_stream.wait_event(consumed[slot])
-            for k, v in host[i % n_batches].items():
-                staging[slot][k].copy_(v, non_blocking=True)
+            staging[slot].buf.copy_(host_slabs[i % n_batches].buf, non_blocking=True)   # ONE H2D copy per step
             ready[slot].record(copy_stream)
 
     upload(0)
@@ -619,18 +625,17 @@ def run_ours(args):
         consumed[slot].record(main)
         loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)      # D2H read of the step's loss (4 bytes)
     e1.record()
-    barrier()
+    torch.cuda.synchronize()          # this rank's own work only: no collective inside the timed region besides the step's
     e2e_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
     last = float(loss_host[-1])
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                          # max over ranks, taken after the timed region
     e2e_s = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _shutdown(eng, world)
         return
     if args.kernel_table:
         kernel_table(eng, resident, args.kernel_table)
@@ -651,14 +656,36 @@ def run_ours(args):
                                      3: "tcgen05-3xTF32 fwd+dgrad+wgrad"}.get(runtime.tc_level(), str(runtime.tc_level())),
                        "cuda_graph": not args.no_graph,
                        "l2": "256 MiB flush write between timed steps, excluded from timing",
-                       "optimizer": "Adam(0.5,0.999), one kernel over the flat parameter bucket", "last_loss": last},
+                       "optimizer": "Adam(0.5,0.999), one kernel over the flat parameter bucket", "last_loss": last,
+                       "ddp": None if world == 1 else {"allreduce_in_graph": bool(eng.graph_has_update) if eng.graph is not None else False,
+                                                       "numa_cpus_per_rank": numa_cpus},
+                       "first_layer": "lifted (no grouped tensor)" if runtime.lift_enabled() else "materialised grouping"},
             "clocks": clocks, "gpu_launches": launches, "wall_s_timed_region": wall,
             "e2e": {"value": pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / args.steps * 1e3},
             "roofline": roof, "roofline_gather": roof_gather, "roofline_backward": roof_bwd, "cpu_baseline": cb}
-    print(json.dumps(line))
-    if world > 1:
+    print(json.dumps(line), flush=True)
+    _shutdown(eng, world)
+
+
+def _shutdown(eng, world):
+    """Leave cleanly under torchrun: drop the captured step graph (it holds NCCL kernels) before the process group goes, and
+    never let a stuck communicator teardown keep the job alive — the JSON line is already out, so a watchdog ends the process."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    if getattr(eng, "graph", None) is not None:
+        eng.graph.reset()
+        eng.graph = None
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
         dist.destroy_process_group()
+    finally:
+        t.cancel()
 
 
 if __name__ == "__main__":

@@ -107,8 +107,11 @@ __global__ void __launch_bounds__(LIFT_THREADS)
             const bool valid = gb + lane < n_groups;
             const int gi = valid ? gb + lane : n_groups - 1;
             const float4 c4 = lv.cc ? ldg4(lv.cc + (size_t)gi * lv.ldz + c) : zero;
-            float4 acc = zero;
+            float4 acc = zero, acc0 = zero;
             const int pb = gi * grp;
+            // ball-query padding repeats a group's FIRST neighbour in every unused slot (pointnet2_ops ball_query), so a
+            // sparse ball sends most of its positions to one row: those are summed in registers and leave as ONE RED
+            const int row0 = __ldg(lv.gidx + pb);
 #pragma unroll 4
             for (int s = 0; s < grp; ++s) {
                 const int p = pb + s;
@@ -123,7 +126,8 @@ __global__ void __launch_bounds__(LIFT_THREADS)
                     dy.x = fmaf(a4.x, g4.x, fmaf(k4.x, v.x, b4.x)); dy.y = fmaf(a4.y, g4.y, fmaf(k4.y, v.y, b4.y));
                     dy.z = fmaf(a4.z, g4.z, fmaf(k4.z, v.z, b4.z)); dy.w = fmaf(a4.w, g4.w, fmaf(k4.w, v.w, b4.w));
                 }
-                if (dz && valid) atomicAdd(reinterpret_cast<float4*>(dz + (size_t)row * lv.ldz + c), dy);   // sm_90+: one vector RED
+                if (row == row0) { acc0.x += dy.x; acc0.y += dy.y; acc0.z += dy.z; acc0.w += dy.w; }
+                else if (dz && valid) atomicAdd(reinterpret_cast<float4*>(dz + (size_t)row * lv.ldz + c), dy);   // sm_90+: one vector RED
                 acc.x += dy.x; acc.y += dy.y; acc.z += dy.z; acc.w += dy.w;
                 if (du && valid) {
                     du4.x = fmaf(sv, dy.x, du4.x); du4.y = fmaf(sv, dy.y, du4.y);
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(LIFT_THREADS)
                     }
                 }
             }
+            if (dz && valid) atomicAdd(reinterpret_cast<float4*>(dz + (size_t)row0 * lv.ldz + c), acc0);
             if (dcc && valid) *reinterpret_cast<float4*>(dcc + (size_t)gi * lv.ldz + c) = make_float4(-acc.x, -acc.y, -acc.z, -acc.w);
         }
     }

@@ -167,8 +167,11 @@ struct TcAct {
 struct TcLift {
     static constexpr int DEPTH = 1;
     LiftView lv; const float* scale; const float* shift; int relu;
+    int la;   // positions between two consecutive fetches of a thread (wgrad: the k-block length; 0: same rows again, next k-block)
     struct Coef { float4 s, t, u; bool on; };
-    template <int R> struct Batch { float4 v[R]; float4 cv[R]; float sv[R]; bool shared; };
+    // nrow / tag: row indices fetched ahead for the NEXT call (tag = its p0 + 1, 0 = none), so that only a thread's first
+    // k-block of a slice / position tile pays the dependent gidx -> Z load chain
+    template <int R> struct Batch { float4 v[R]; float4 cv[R]; float sv[R]; int nrow[R]; int tag; bool shared; };
     __device__ __forceinline__ Coef prep(int k, int K) const {
         Coef c;
         c.on = k < K;
@@ -182,7 +185,10 @@ struct TcLift {
     __device__ __forceinline__ void fetch(Batch<R>& b, int p0, int stride, int P, int k, int K) const {
         const int kk = k < K ? k : 0;
         int row[R];
-        if (R == 4 && stride == 1 && (p0 & 3) == 0 && p0 + 3 < P) {
+        if (b.tag == p0 + 1) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) row[i] = b.nrow[i];
+        } else if (R == 4 && stride == 1 && (p0 & 3) == 0 && p0 + 3 < P) {
             const int4 r4 = __ldg(reinterpret_cast<const int4*>(lv.gidx + p0));
             row[0] = r4.x; row[R > 1 ? 1 : 0] = r4.y; row[R > 2 ? 2 : 0] = r4.z; row[R > 3 ? 3 : 0] = r4.w;
         } else {
@@ -194,6 +200,19 @@ struct TcLift {
         }
 #pragma unroll
         for (int i = 0; i < R; ++i) b.v[i] = ld4g(lv.z + (size_t)row[i] * lv.ldz + kk);
+        if (la == 0) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) b.nrow[i] = row[i];
+            b.tag = p0 + 1;
+        } else {
+            const int pn = p0 + la;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int p = pn + i * stride;
+                b.nrow[i] = __ldg(lv.gidx + (p < P ? p : P - 1));
+            }
+            b.tag = pn + 1;
+        }
         b.shared = false;
         if (lv.cc) {
             const int pf = p0 < P ? p0 : P - 1;
@@ -705,13 +724,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         };
         Cur c0{(int)blockIdx.x, 0, 0};
         if (c0.t < n_ptiles) c0.p0 = tile_of(c0.t) * TC_N;
-        Batch4 r0;
+        Batch4 r0{};      // value-initialised: TcLift keeps a look-ahead tag in the batch
         typename BLoad::Coef f0 = bl.prep(chunk * 4, K);
         issue(r0, f0, c0);
         if constexpr (BLoad::DEPTH == 2 && MT == 2) {   // measured: +5 % on the 256-channel layers, -8 % on the narrow ones
             Cur c1 = c0;
             if (c1.t < n_ptiles) advance(c1);
-            Batch4 r1;
+            Batch4 r1{};
             typename BLoad::Coef f1 = f0;
             issue(r1, f1, c1);
             while (c0.t < n_ptiles) {
@@ -1331,7 +1350,7 @@ int launch_wgrad1(const TcDy& da, const XB& xb, int P, int Cout, int Cin, float*
 inline TcLift make_tclift(const o3d_lift_t* lf, const int32_t* gidx, const float* scale, const float* shift, int relu) {
     int gsh = 0;
     while ((2 << gsh) <= lf->grp) ++gsh;
-    return TcLift{LiftView{lf->z, lf->ldz, gidx, lf->cc, gsh, lf->s, lf->u}, scale, shift, relu};
+    return TcLift{LiftView{lf->z, lf->ldz, gidx, lf->cc, gsh, lf->s, lf->u}, scale, shift, relu, 0};
 }
 }  // namespace
 
@@ -1411,7 +1430,8 @@ extern "C" int o3d_pw_wgrad_tc_lift(const float* g, int ldg, const float* y, int
                 "o3d_pw_wgrad_tc_lift: channel counts / leading dimensions");
     if (P == 0) return O3D_OK;
     TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1), g_tc_debug};
-    const TcLift xb = make_tclift(lf, gidx, in_scale, in_shift, in_relu);
+    TcLift xb = make_tclift(lf, gidx, in_scale, in_shift, in_relu);
+    xb.la = part ? WG2_K : TC_K;      // a producer thread's next fetch lies one k-block of positions further
     if (part) return dispatch_wgrad2(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, (cudaStream_t)stream);
     return launch_wgrad1(da, xb, P, Cout, Cin, dw, lddw, (cudaStream_t)stream);
 }

@@ -12,6 +12,39 @@ import torch
 from . import _lib, ddp, ops
 
 
+class BatchSlab:
+    """A batch dict laid out in ONE contiguous byte buffer (every tensor a 256-byte-aligned view of it): a step's inputs
+    move host -> device (pinned slab -> device slab) and device -> static graph inputs with one copy each instead of one
+    per tensor — at a few milliseconds per step seven small copies per hop are visible, and under DDP eight processes
+    issuing them skew the ranks."""
+
+    def __init__(self, spec, device, pin=False):
+        self.spec = spec                                          # [(key, shape, dtype, offset, nbytes)]
+        total = spec[-1][3] + spec[-1][4] if spec else 0
+        self.buf = torch.empty(total, dtype=torch.uint8, device=device)
+        if pin and self.buf.device.type == "cpu":
+            self.buf = self.buf.pin_memory()
+        self.tensors = {k: self.buf[off:off + nb].view(dt).view(shape) for k, shape, dt, off, nb in spec}
+        self.nbytes = total
+
+    @classmethod
+    def like(cls, batch, device, pin=False):
+        spec, off = [], 0
+        for k, v in batch.items():
+            nb = v.numel() * v.element_size()
+            spec.append((k, tuple(v.shape), v.dtype, off, nb))
+            off += (nb + 255) & ~255
+        return cls(spec, device, pin)
+
+    def load(self, batch):
+        for k, v in batch.items():
+            self.tensors[k].copy_(v, non_blocking=True)
+        return self
+
+    def sibling(self, device, pin=False):
+        return BatchSlab(self.spec, device, pin)
+
+
 class FlatAdam:
     """Adam over `FlatParams` with the step counter and learning rate in device memory (graph-replayable)."""
 
@@ -34,8 +67,9 @@ class FlatAdam:
 class TrainStep:
     """`step(batch) -> loss` for a model exposing `training_step(batch, idx)`; `batch` is a dict of device tensors."""
 
-    def __init__(self, model, lr=1e-3, weight_decay=0.0, use_graph=True, warmup=3):
+    def __init__(self, model, lr=1e-3, weight_decay=0.0, use_graph=True, warmup=3, capture_collective=True):
         self.model = model
+        self.capture_collective = capture_collective
         self.flat = ddp.FlatParams(model)
         ddp.broadcast_parameters(self.flat, model)
         self.opt = FlatAdam(self.flat, lr=lr, weight_decay=weight_decay)
@@ -57,12 +91,19 @@ class TrainStep:
         self.opt.step()
 
     def _eager(self, batch):
+        if isinstance(batch, BatchSlab):
+            batch = batch.tensors
         loss = self._fwd_bwd(batch)
         self._finish()
         return loss
 
     def _capture(self, batch):
-        self.static_batch = {k: v.clone() for k, v in batch.items()}
+        # static inputs live in ONE slab, so a step's batch arrives with a single copy (BatchSlab) instead of one per tensor
+        if isinstance(batch, BatchSlab):
+            batch = batch.tensors
+        self.static_slab = BatchSlab.like(batch, device=self.flat.flat.device)
+        self.static_slab.load(batch)
+        self.static_batch = self.static_slab.tensors
         # settle allocator / lazy initialisation on a side stream, WITHOUT advancing training: parameters, optimizer
         # state and BatchNorm buffers are snapshotted and restored around the two throw-away steps
         buffers = list(self.model.buffers())
@@ -79,14 +120,27 @@ class TrainStep:
             self.opt.state.copy_(snap[3])
             for b, old in zip(buffers, snap[4]):
                 b.copy_(old)
-        # single rank: the whole step (incl. Adam) is one graph; multi-rank: forward+backward are captured and the
-        # gradient all-reduce + Adam are enqueued right behind the replay (NCCL stays outside the capture)
-        self.graph = torch.cuda.CUDAGraph()
-        self.graph_has_update = not ddp.is_distributed()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._fwd_bwd(self.static_batch)
-            if self.graph_has_update:
-                self._finish()
+        # The whole step — zero-grad, forward, backward, the NCCL all-reduce of the flat bucket and Adam — is ONE graph, also
+        # under DDP: nothing trails the replay.  NCCL collectives are capturable; the capture runs in thread-local error mode so
+        # that the process group's watchdog thread (which polls CUDA events) cannot invalidate it.  Should a NCCL / torch build
+        # refuse the capture, the collective and Adam fall back to being enqueued right behind the replay.
+        self.graph_has_update = True
+        if ddp.is_distributed() and not self.capture_collective:
+            self.graph_has_update = False
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.static_loss = self._fwd_bwd(self.static_batch)
+                if self.graph_has_update:
+                    self._finish()
+        except Exception:
+            if not (ddp.is_distributed() and self.graph_has_update):
+                raise
+            torch.cuda.synchronize()
+            self.graph_has_update = False
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.static_loss = self._fwd_bwd(self.static_batch)
 
     def step(self, batch):
         self.calls += 1
@@ -94,8 +148,11 @@ class TrainStep:
             return self._eager(batch)
         if self.graph is None:
             self._capture(batch)
-        for k, v in batch.items():
-            self.static_batch[k].copy_(v, non_blocking=True)
+        if isinstance(batch, BatchSlab):
+            self.static_slab.buf.copy_(batch.buf, non_blocking=True)      # ONE device copy for the whole batch
+        else:
+            for k, v in batch.items():
+                self.static_batch[k].copy_(v, non_blocking=True)
         self.graph.replay()
         if not self.graph_has_update:
             self._finish()
