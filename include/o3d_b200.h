@@ -115,6 +115,24 @@ int o3d_group_rows(const float* feat_cl, const int32_t* idx, int B, int N, int L
 int o3d_group_rows_grad(const float* grad_out_cl, const int32_t* idx, int B, int N, int L, int C, float* grad_feat_cl,
                         void* stream);
 
+/* Cross-correlation front ends (models/head/xcorr.py).  The MLP + max-pool behind either of them is a lifted stack
+ * (o3d_lift_t below), which also provides the gradient of the BoxAware grouping (indices carry no gradient).
+ *
+ * o3d_xcorr_boxaware_fwd — BoxAwareXCorr (xcorr.py:81-88: cdist + argsort + [:k]): template_bc (B,M,D), search_bc (B,N,D),
+ *   D <= 16, k <= 8 -> idx (B,N,k): the k template points with the nearest box cloud per search point, nearest first,
+ *   equal distances in ascending template order; squared distances by direct differences (see csrc/xcorr.cu).
+ * o3d_xcorr_p2b_fwd — P2B_XCorr's cosine map (xcorr.py:37-38): tfeat_cl (B,n1,C), sfeat_cl (B,n2,C) channels-last
+ *   -> sim (B,n2,n1) = <t_i / max(|t_i|, eps), s_j / max(|s_j|, eps)>; tnorm (B,n1) / snorm (B,n2) (nullable) keep the
+ *   norms for the backward.
+ * o3d_xcorr_p2b_bwd — dsim (B,n2,n1) -> d_tfeat_cl (B,n1,C), d_sfeat_cl (B,n2,C) (either may be NULL; plain stores).   */
+int o3d_xcorr_boxaware_fwd(const float* template_bc, const float* search_bc, int B, int M, int N, int D, int k, int32_t* idx,
+                           void* stream);
+int o3d_xcorr_p2b_fwd(const float* tfeat_cl, const float* sfeat_cl, int B, int n1, int n2, int C, float eps, float* sim,
+                      float* tnorm, float* snorm, void* stream);
+int o3d_xcorr_p2b_bwd(const float* dsim, const float* sim, const float* tfeat_cl, const float* sfeat_cl, const float* tnorm,
+                      const float* snorm, int B, int n1, int n2, int C, float eps, float* d_tfeat_cl, float* d_sfeat_cl,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Block 3 — point-wise MLP layers (SharedMLP / Seq of the reference: 1x1 conv + BatchNorm + ReLU
  * [+ max-pool over nsample / k / template points]; pointnet2/utils/pytorch_utils.py:12-37,68-121,
@@ -195,31 +213,31 @@ int o3d_pw_dgrad_tc(const float* g, int ldg, const float* y, int ldy, const floa
 /* "Lifted" first layer.  When the first 1x1 convolution of a stack acts on GROUPED rows — QueryAndGroup
  * (pointnet2_utils.py:317-329: [xyz(idx) - centre, features(idx)]), BoxAwareXCorr's top-k grouping (xcorr.py:87-90) or
  * P2B_XCorr's [similarity, template xyz, template feature] fusion tensor (xcorr.py:39-46) — its linearity lets the
- * convolution run ONCE per source point instead of once per (centre, neighbour) position:
- *     Y0[p, c] = Z[row(p), c] - cc[p / grp, c] + s[p] * u[c]
- *       Z  = W0 . source rows           (zrows x C0, computed by an ordinary one-layer stack over the source points)
- *       cc = W0_xyz . centre            (SA layers; NULL otherwise)
- *       s  = per-position scalar, u = its weight column (P2B's similarity channel; NULL otherwise)
+ * feature part of the convolution run ONCE per source point instead of once per (centre, neighbour) position:
+ *     Y0[p, c] = Z[row(p), c] + s[p][0] * u[0][c] + s[p][1] * u[1][c] + s[p][2] * u[2][c] + s[p][3] * u[3][c]
+ *       Z = W0_f . source features  (zrows x C0, computed by an ordinary one-layer stack over the source points; optional)
+ *       s = up to four per-position scalars with their weight columns u: the relative coordinates (dx, dy, dz) of a set
+ *           abstraction layer — applied directly, in the reference's difference-then-multiply form — or P2B's cosine
+ *           similarity (optional)
  * Neither the grouped tensor nor Y0 is written to memory: Y0 exists only inside the operand loaders / epilogues of
  * the next layer's GEMMs (tensor-core path), its batch statistics come from one gather pass, and the backward is a
- * scatter of dY0 into dZ / dcc / ds / du.  Layer 0 of the descriptor then carries only BatchNorm / ReLU (weight NULL).
+ * scatter of dY0 into dZ / ds / du.  Layer 0 of the descriptor then carries only BatchNorm / ReLU (weight NULL).
  * row(p) = cloud(p) * rows_per_cloud + (ridx ? ridx[p] : p % ridx_mod),  cloud(p) = p / pos_per_cloud.             */
 typedef struct o3d_lift_t {
-    const float* z;        /* [zrows, ldz], ldz == round4(C0)                                         */
+    const float* z;        /* [zrows, ldz], ldz == round4(C0), or NULL (no gathered part)             */
     int ldz;
     const int32_t* ridx;   /* [P] source row of each position, local to its cloud, or NULL            */
     int ridx_mod;          /* used when ridx == NULL                                                  */
     int rows_per_cloud;    /* Z rows per cloud                                                        */
     int pos_per_cloud;     /* positions per cloud                                                     */
-    const float* cc;       /* [P / grp, ldz] or NULL                                                  */
-    int grp;               /* positions per cc row (power of two); also the scatter kernel's work unit */
-    const float* s;        /* [P] or NULL                                                             */
-    const float* u;        /* [ldz] or NULL                                                           */
-    /* backward outputs (NULL = not wanted); d_z, d_s, d_u must be zero-filled by the caller          */
+    int grp;               /* work unit of the gather / scatter passes: consecutive positions per thread (power of two
+                              dividing P; the ball-query group size, so that first-hit padding merges)               */
+    const float* s;        /* [P, 4] (unused columns zero) or NULL                                    */
+    const float* u;        /* [4, ldz] (unused rows zero) or NULL                                     */
+    /* backward outputs (NULL = not wanted), all zero-filled by the caller                           */
     float* d_z;            /* [zrows, ldz]   += scatter of dY0                                        */
-    float* d_cc;           /* [P / grp, ldz]  = -sum over the group of dY0                            */
-    float* d_s;            /* [P]            += dY0 . u                                               */
-    float* d_u;            /* [ldz]          += sum_p s[p] * dY0[p]                                   */
+    float* d_s;            /* [P, 4]         += dY0 . u[j]                                            */
+    float* d_u;            /* [4, ldz]       += sum_p s[p][j] * dY0[p]                                */
 } o3d_lift_t;
 
 typedef struct o3d_stack_t {

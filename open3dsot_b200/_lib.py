@@ -35,6 +35,9 @@ PROTOTYPES = {
     "o3d_three_nn_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "o3d_group_rows": [_p, _p, _i, _i, _i, _i, _p, _p],
     "o3d_group_rows_grad": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "o3d_xcorr_boxaware_fwd": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "o3d_xcorr_p2b_fwd": [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p],
+    "o3d_xcorr_p2b_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "o3d_pw_fwd": [_p, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p],
     "o3d_pw_dgrad": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _p, _p,
                      _p],
@@ -80,8 +83,8 @@ _I8, _F8, _P8 = ctypes.c_int * MAX_LAYERS, ctypes.c_float * MAX_LAYERS, ctypes.c
 class LiftDesc(ctypes.Structure):
     """ctypes mirror of `o3d_lift_t` (include/o3d_b200.h, block 4)."""
     _fields_ = [("z", _p), ("ldz", _i), ("ridx", _p), ("ridx_mod", _i), ("rows_per_cloud", _i), ("pos_per_cloud", _i),
-                ("cc", _p), ("grp", _i), ("s", _p), ("u", _p),
-                ("d_z", _p), ("d_cc", _p), ("d_s", _p), ("d_u", _p)]
+                ("grp", _i), ("s", _p), ("u", _p),
+                ("d_z", _p), ("d_s", _p), ("d_u", _p)]
 
 
 class StackDesc(ctypes.Structure):

@@ -160,94 +160,83 @@ struct TcAct {
 };
 
 // Lifted first layer as an operand (include/o3d_b200.h: o3d_lift_t): row p of the "activation matrix" is
-//     relu(bn(Y0[p])),  Y0[p, k] = Z[gidx[p], k] - cc[p >> gsh, k] + s[p] * u[k]
+//     relu(bn(Y0[p])),  Y0[p, k] = Z[gidx[p], k] + sum_j s[p][j] * u[j][k]
 // gathered from the (L2-resident) source-point matrix Z — the grouped tensor and Y0 itself are never stored.
-// Same interface as TcAct; loads stay "raw-first": gidx -> Z row (two dependent loads, the index re-reads hit L1 from the
-// second k-block of a tile on), the subtraction / BN / ReLU happen in finish().
+// Same interface as TcAct; loads stay "raw-first": gidx -> Z row (two dependent loads; the row indices are fetched one call
+// ahead), the s.u terms / BN / ReLU happen in finish().
 struct TcLift {
     static constexpr int DEPTH = 1;
     LiftView lv; const float* scale; const float* shift; int relu;
     int la;   // positions between two consecutive fetches of a thread (wgrad: the k-block length; 0: same rows again, next k-block)
-    struct Coef { float4 s, t, u; bool on; };
+    struct Coef { float4 s, t, u0, u1, u2, u3; bool on; };
     // nrow / tag: row indices fetched ahead for the NEXT call (tag = its p0 + 1, 0 = none), so that only a thread's first
     // k-block of a slice / position tile pays the dependent gidx -> Z load chain
-    template <int R> struct Batch { float4 v[R]; float4 cv[R]; float sv[R]; int nrow[R]; int tag; bool shared; };
+    template <int R> struct Batch { float4 v[R]; float4 sv[R]; int nrow[R]; int tag; };
     __device__ __forceinline__ Coef prep(int k, int K) const {
         Coef c;
         c.on = k < K;
         c.s = make_float4(1.f, 1.f, 1.f, 1.f);
-        c.t = c.u = make_float4(0.f, 0.f, 0.f, 0.f);
+        c.t = c.u0 = c.u1 = c.u2 = c.u3 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c.on && scale) { c.s = ld4g(scale + k); c.t = ld4g(shift + k); }
-        if (c.on && lv.u) c.u = ld4g(lv.u + k);
+        if (c.on && lv.u) { c.u0 = ld4g(lv.u + k); c.u1 = ld4g(lv.u + lv.ldz + k); c.u2 = ld4g(lv.u + 2 * lv.ldz + k); c.u3 = ld4g(lv.u + 3 * lv.ldz + k); }
         return c;
     }
     template <int R>
     __device__ __forceinline__ void fetch(Batch<R>& b, int p0, int stride, int P, int k, int K) const {
         const int kk = k < K ? k : 0;
-        int row[R];
-        if (b.tag == p0 + 1) {
+        if (lv.z) {
+            int row[R];
+            if (b.tag == p0 + 1) {
 #pragma unroll
-            for (int i = 0; i < R; ++i) row[i] = b.nrow[i];
-        } else if (R == 4 && stride == 1 && (p0 & 3) == 0 && p0 + 3 < P) {
-            const int4 r4 = __ldg(reinterpret_cast<const int4*>(lv.gidx + p0));
-            row[0] = r4.x; row[R > 1 ? 1 : 0] = r4.y; row[R > 2 ? 2 : 0] = r4.z; row[R > 3 ? 3 : 0] = r4.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int p = p0 + i * stride;
-                row[i] = __ldg(lv.gidx + (p < P ? p : P - 1));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < R; ++i) b.v[i] = ld4g(lv.z + (size_t)row[i] * lv.ldz + kk);
-        if (la == 0) {
-#pragma unroll
-            for (int i = 0; i < R; ++i) b.nrow[i] = row[i];
-            b.tag = p0 + 1;
-        } else {
-            const int pn = p0 + la;
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int p = pn + i * stride;
-                b.nrow[i] = __ldg(lv.gidx + (p < P ? p : P - 1));
-            }
-            b.tag = pn + 1;
-        }
-        b.shared = false;
-        if (lv.cc) {
-            const int pf = p0 < P ? p0 : P - 1;
-            const int pe = p0 + (R - 1) * stride;
-            const int pl = pe < P ? pe : P - 1;
-            if ((pf >> lv.gsh) == (pl >> lv.gsh)) {
-                b.shared = true;
-                b.cv[0] = ld4g(lv.cc + (size_t)(pf >> lv.gsh) * lv.ldz + kk);
+                for (int i = 0; i < R; ++i) row[i] = b.nrow[i];
+            } else if (R == 4 && stride == 1 && (p0 & 3) == 0 && p0 + 3 < P) {
+                const int4 r4 = __ldg(reinterpret_cast<const int4*>(lv.gidx + p0));
+                row[0] = r4.x; row[R > 1 ? 1 : 0] = r4.y; row[R > 2 ? 2 : 0] = r4.z; row[R > 3 ? 3 : 0] = r4.w;
             } else {
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
                     const int p = p0 + i * stride;
-                    b.cv[i] = ld4g(lv.cc + (size_t)((p < P ? p : P - 1) >> lv.gsh) * lv.ldz + kk);
+                    row[i] = __ldg(lv.gidx + (p < P ? p : P - 1));
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i) b.v[i] = ld4g(lv.z + (size_t)row[i] * lv.ldz + kk);
+            if (la == 0) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) b.nrow[i] = row[i];
+                b.tag = p0 + 1;
+            } else {
+                const int pn = p0 + la;
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const int p = pn + i * stride;
+                    b.nrow[i] = __ldg(lv.gidx + (p < P ? p : P - 1));
+                }
+                b.tag = pn + 1;
             }
         }
         if (lv.s) {
 #pragma unroll
             for (int i = 0; i < R; ++i) {
                 const int p = p0 + i * stride;
-                b.sv[i] = __ldg(lv.s + (p < P ? p : P - 1));
+                b.sv[i] = ld4g(lv.s + (size_t)(p < P ? p : P - 1) * 4);
             }
         }
     }
     template <int R>
     __device__ __forceinline__ float4 finish(const Batch<R>& b, const Coef& c, int i, int p, int P) const {
-        if (!(c.on && p < P)) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 cv = lv.cc ? (b.shared ? b.cv[0] : b.cv[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 v = lift_val4(b.v[i], cv, lv.s ? b.sv[i] : 0.f, c.u);
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(c.on && p < P)) return zero;
+        float4 v = lift_val4(lv.z ? b.v[i] : zero, lv.s ? b.sv[i] : zero, c.u0, c.u1, c.u2, c.u3);
         if (scale) { v.x = fmaf(v.x, c.s.x, c.t.x); v.y = fmaf(v.y, c.s.y, c.t.y); v.z = fmaf(v.z, c.s.z, c.t.z); v.w = fmaf(v.w, c.s.w, c.t.w); }
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         return v;
     }
-    __device__ __forceinline__ void prefetch_rows(int p0, int rows, int P) const {   // the index slice; Z itself lives in L2
-        if (p0 < P) o3d_prefetch_l2(lv.gidx + p0, (size_t)min(rows, P - p0) * sizeof(int32_t));
+    __device__ __forceinline__ void prefetch_rows(int p0, int rows, int P) const {   // index / scalar slices; Z itself lives in L2
+        if (p0 >= P) return;
+        const size_t n = (size_t)min(rows, P - p0);
+        if (lv.z) o3d_prefetch_l2(lv.gidx + p0, n * sizeof(int32_t));
+        if (lv.s) o3d_prefetch_l2(lv.s + (size_t)p0 * 4, n * 16);
     }
 };
 
@@ -434,41 +423,44 @@ struct TcFwdEpi {
 };
 
 // LD: compile-time row stride shared by out and yprev (0 = use the runtime ldo / ldyp)
-template <int LD>
+// LIFT: the previous layer is a lifted one (its raw output is re-evaluated from Z / s.u); a separate instantiation so that the
+// ordinary dgrad kernels carry none of its state
+template <int LD, bool LIFT = false>
 struct TcDgradEpi {
     float* out; int ldo; const float* yprev; int ldyp; const float* scale; const float* shift; int relu;
     double* s1g; double* s2y;
-    LiftView lv;             // lv.gidx != nullptr: the previous layer's raw output is the lifted Y0 (gathered, never stored)
+    LiftView lv;             // lv.z / lv.s set: the previous layer's raw output is the lifted Y0 (re-evaluated, never stored)
     float sc, sh; double d1, d2;
     float yv[16];
-    float uch; const int32_t* gs;   // lifted: this thread's u[ch]; the tile's gidx slice staged in shared memory
+    float u0, u1, u2, u3; const int32_t* gs;   // lifted: this thread's u[j][ch]; the tile's gidx slice staged in shared memory
+    __device__ __forceinline__ bool lifted() const { return LIFT; }
     __device__ __forceinline__ void begin(int ch, int Nw) {
         d1 = d2 = 0.0;
         sc = (scale && ch < Nw) ? scale[ch] : 1.f;
         sh = (shift && ch < Nw) ? shift[ch] : 0.f;
-        uch = (lv.gidx && lv.u && ch < Nw) ? lv.u[ch] : 0.f;
-        gs = nullptr;
+        if constexpr (LIFT) {
+            const bool on = lv.u && ch < Nw;
+            u0 = on ? lv.u[ch] : 0.f; u1 = on ? lv.u[lv.ldz + ch] : 0.f; u2 = on ? lv.u[2 * lv.ldz + ch] : 0.f; u3 = on ? lv.u[3 * lv.ldz + ch] : 0.f;
+            gs = nullptr;
+        }
     }
-    __device__ __forceinline__ const int32_t* lift_gidx() const { return lv.gidx; }
-    __device__ __forceinline__ void set_tile(const int32_t* g) { gs = g; }
+    __device__ __forceinline__ const int32_t* lift_gidx() const { return LIFT ? lv.gidx : nullptr; }
+    __device__ __forceinline__ void set_tile(const int32_t* g) { if constexpr (LIFT) gs = g; }
     // lifted yprev: `col` = first column of the group inside the tile (index into the staged gidx slice)
     __device__ __forceinline__ void prefetch_lift(int ch, int pbase, int col, int P) {
-        const bool one_grp = lv.cc && lv.gsh >= 4;                      // the 16 positions share one cc row
-        const float ccv = one_grp ? __ldg(lv.cc + (size_t)(pbase >> lv.gsh) * lv.ldz + ch) : 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int pj = min(pbase + j, P - 1);
-            const float z = __ldg(lv.z + (size_t)gs[col + j] * lv.ldz + ch);
-            const float c = lv.cc ? (one_grp ? ccv : __ldg(lv.cc + (size_t)(pj >> lv.gsh) * lv.ldz + ch)) : 0.f;
-            const float sv = lv.s ? __ldg(lv.s + pj) : 0.f;
-            yv[j] = lift_val(z, c, sv, uch);
+            const float z = lv.z ? __ldg(lv.z + (size_t)gs[col + j] * lv.ldz + ch) : 0.f;
+            const float4 sv = lv.s ? ld4g(lv.s + (size_t)pj * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            yv[j] = lift_val(z, sv, u0, u1, u2, u3);
         }
     }
     // (an L2 prefetch of these rows one tile ahead was measured: 7-15 % slower, it competes with the loader's own window)
     // issue the previous layer's raw outputs for this column group before waiting on TMEM (independent loads)
     __device__ __forceinline__ void prefetch(int ch, int Nw, int pbase, int P) {
         if (ch >= Nw) return;
-        if (lv.gidx) { prefetch_lift(ch, pbase, pbase & (TC_N - 1), P); return; }
+        if constexpr (LIFT) { prefetch_lift(ch, pbase, pbase & (TC_N - 1), P); return; }
         if (!yprev) return;
         if (pbase + 16 <= P) {
             const float* yp = yprev + (size_t)pbase * ldyp + ch;
@@ -491,7 +483,7 @@ struct TcDgradEpi {
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            if (yprev || lv.gidx) {
+            if (yprev || lifted()) {
                 if (relu) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaf(yv[j], sc, sh) > 0.f ? v[j] : 0.f;
@@ -510,7 +502,7 @@ struct TcDgradEpi {
             for (int j = 0; j < 16; ++j) {
                 if (pbase + j >= P) break;
                 float v = __uint_as_float(r[j]);
-                if (yprev || lv.gidx) {
+                if (yprev || lifted()) {
                     if (relu && !(fmaf(yv[j], sc, sh) > 0.f)) v = 0.f;
                     s2 = fmaf(v, yv[j], s2);
                 }
@@ -1231,11 +1223,15 @@ int launch_fwd(const BLoad& bl, const void* wtiles, const float* bias, int P, in
     return launch_tc<MTMASK>(bl, (const uint8_t*)wtiles, P, K, Nw, ep, st, "o3d_pw_fwd_tc");
 }
 
-template <int LD, int MTMASK>
+template <int LD, int MTMASK, bool LIFT = false>
 int launch_dgrad(const TcDy& bl, const void* wtiles_t, int P, int Cout, int Cin, float* out, int ldo, const float* yprev,
                  int ldyp, const float* pscale, const float* pshift, int prelu, double* s1, double* s2y, cudaStream_t st,
                  const LiftView* lv = nullptr) {
-    TcDgradEpi<LD> ep{};
+    if constexpr (!LIFT) {
+        if (lv) return launch_dgrad<LD, MTMASK, true>(bl, wtiles_t, P, Cout, Cin, out, ldo, yprev, ldyp, pscale, pshift, prelu, s1, s2y,
+                                                      st, lv);
+    }
+    TcDgradEpi<LD, LIFT> ep{};
     if (lv) ep.lv = *lv;
     ep.out = out; ep.ldo = ldo; ep.yprev = yprev; ep.ldyp = ldyp; ep.scale = pscale; ep.shift = pshift; ep.relu = prelu;
     ep.s1g = s1; ep.s2y = s2y;
@@ -1324,10 +1320,8 @@ extern "C" int o3d_pw_dgrad_tc_lift(const float* g, int ldg, const float* y, int
                                     const void* wtiles_t, int P, int Cout, int Cin, float* out, int ldo,
                                     const o3d_lift_t* lf, const int32_t* gidx, const float* pscale, const float* pshift,
                                     int prelu, double* s1, double* s2y, void* stream) {
-    O3D_REQUIRE(lf && gidx && lf->ldz == Cin, O3D_ERR_ARG, "o3d_pw_dgrad_tc_lift: lift descriptor");
-    int gsh = 0;
-    while ((2 << gsh) <= lf->grp) ++gsh;
-    const LiftView lv{lf->z, lf->ldz, gidx, lf->cc, gsh, lf->s, lf->u};
+    O3D_REQUIRE(lf && (gidx || !lf->z) && (lf->z || lf->s) && lf->ldz == Cin, O3D_ERR_ARG, "o3d_pw_dgrad_tc_lift: lift descriptor");
+    const LiftView lv{lf->z, lf->ldz, lf->z ? gidx : nullptr, lf->s, lf->u};
     return dgrad_tc_impl(g, ldg, y, ldy, a, b, cc, dpool, sel, S, ldp, wtiles_t, P, Cout, Cin, out, ldo, nullptr, 0, pscale,
                          pshift, prelu, s1, s2y, stream, &lv);
 }
@@ -1348,9 +1342,7 @@ int launch_wgrad1(const TcDy& da, const XB& xb, int P, int Cout, int Cin, float*
     return O3D_OK;
 }
 inline TcLift make_tclift(const o3d_lift_t* lf, const int32_t* gidx, const float* scale, const float* shift, int relu) {
-    int gsh = 0;
-    while ((2 << gsh) <= lf->grp) ++gsh;
-    return TcLift{LiftView{lf->z, lf->ldz, gidx, lf->cc, gsh, lf->s, lf->u}, scale, shift, relu, 0};
+    return TcLift{LiftView{lf->z, lf->ldz, lf->z ? gidx : nullptr, lf->s, lf->u}, scale, shift, relu, 0};
 }
 }  // namespace
 
@@ -1425,7 +1417,7 @@ extern "C" int o3d_pw_wgrad_tc_lift(const float* g, int ldg, const float* y, int
                                     const o3d_lift_t* lf, const int32_t* gidx, const float* in_scale, const float* in_shift,
                                     int in_relu, int P, int Cout, int Cin, float* dw, int lddw, float* part,
                                     long long part_floats, void* stream) {
-    O3D_REQUIRE((g || dpool) && lf && gidx && dw, O3D_ERR_ARG, "o3d_pw_wgrad_tc_lift: null pointer");
+    O3D_REQUIRE((g || dpool) && lf && (gidx || !lf->z) && dw, O3D_ERR_ARG, "o3d_pw_wgrad_tc_lift: null pointer");
     O3D_REQUIRE((Cout & 3) == 0 && (Cin & 3) == 0 && lf->ldz == Cin && (lddw & 3) == 0, O3D_ERR_ARG,
                 "o3d_pw_wgrad_tc_lift: channel counts / leading dimensions");
     if (P == 0) return O3D_OK;
@@ -1440,9 +1432,8 @@ extern "C" int o3d_pw_fwd_tc_lift(const o3d_lift_t* lf, const int32_t* gidx, con
                                   int in_relu, const void* wtiles, const float* bias, int P, int K, int N, float* y, int ldy,
                                   double* sum, double* sumsq, int S, float* ymax, float* ymin, int32_t* arg, int ldp,
                                   void* stream) {
-    O3D_REQUIRE(lf && gidx && wtiles, O3D_ERR_ARG, "o3d_pw_fwd_tc_lift: null pointer");
+    O3D_REQUIRE(lf && (gidx || !lf->z) && wtiles, O3D_ERR_ARG, "o3d_pw_fwd_tc_lift: null pointer");
     O3D_REQUIRE(P >= 0 && K >= 32 && N >= 1 && (K & 3) == 0 && lf->ldz == K, O3D_ERR_ARG, "o3d_pw_fwd_tc_lift: bad sizes");
-    O3D_REQUIRE(lf->cc == nullptr || lf->grp >= 4, O3D_ERR_ARG, "o3d_pw_fwd_tc_lift: grp must be >= 4");
     O3D_REQUIRE(S == 0 || (P % S == 0 && 64 % S == 0 && ymax && ymin && arg), O3D_ERR_ARG,
                 "o3d_pw_fwd_tc_lift: pooling group size must divide 64 and P");
     if (P == 0) return O3D_OK;

@@ -153,8 +153,7 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     if (p.lift) {
         // Y0 stays virtual when all three GEMMs of layer 1 run on the tensor cores over whole 32-channel k-blocks
         const bool tcw1 = (d->use_tc & 2) && p.Nw[1] >= 64 && p.K[1] >= 64 && d->P >= 4096;
-        p.virt = p.tc_f[1] && p.tc_b[1] && tcw1 && tc_main(p.K[1]) == p.K[1] && p.K[1] % 32 == 0 &&
-                 (d->lift->cc == nullptr || d->lift->grp >= 4) && !(d->use_tc & 8);
+        p.virt = p.tc_f[1] && p.tc_b[1] && tcw1 && tc_main(p.K[1]) == p.K[1] && p.K[1] % 32 == 0 && !(d->use_tc & 8);
     }
     // statistics block first (one memset)
     p.stat_all = o;
@@ -169,7 +168,7 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
         p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(tc_main(p.K[l]), p.Nw[l]));
         p.y[l] = o; if (!(l == 0 && p.virt)) o += al(sizeof(float) * (size_t)p.P * p.Nw[l]);
     }
-    p.gidx = o; if (p.lift) o += al(sizeof(int32_t) * (size_t)p.P);
+    p.gidx = o; if (p.lift && d->lift->z) o += al(sizeof(int32_t) * (size_t)p.P);
     const size_t gsz = al(sizeof(float) * (size_t)p.rows * p.Nw[p.n - 1]);
     p.ymax = o; o += p.S > 0 ? gsz : 0;
     p.ymin = o; o += p.S > 0 ? gsz : 0;
@@ -369,7 +368,7 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         if (l == 0 && p.lift) {
             // the lifted layer has no GEMM: dY0 = a*g + b + cc*Y0 is scattered into dZ / dcc / ds / du
             const o3d_lift_t* lf = d->lift;
-            if (lf->d_z || lf->d_cc || lf->d_s || lf->d_u) {
+            if (lf->d_z || lf->d_s || lf->d_u) {
                 rc = o3d_lift_scatter(lf, p.P, Nl, at<int32_t>(wf, p.gidx), p.virt ? nullptr : at<float>(wf, p.y[0]), g, Nl, a, b,
                                       cc, stream);
                 if (rc) return rc;

@@ -173,7 +173,7 @@ class _MLPStackFn(torch.autograd.Function):
 
 # ---------------------------------------------------------------------------------------------- lifted first layer
 class _LiftGeom:
-    """Static geometry of a lifted stack: Y0[p] = Z[cloud(p) * rows_per_cloud + (ridx[p] | p % ridx_mod)] - cc[p // grp] + s[p] * u."""
+    """Static geometry of a lifted stack: Y0[p] = Z[cloud(p) * rows_per_cloud + (ridx[p] | p % ridx_mod)] + s[p] . u."""
     __slots__ = ("P", "ridx_mod", "rows_per_cloud", "pos_per_cloud", "grp")
 
     def __init__(self, P, ridx_mod, rows_per_cloud, pos_per_cloud, grp):
@@ -181,20 +181,22 @@ class _LiftGeom:
 
 
 class _LiftedStackFn(torch.autograd.Function):
-    """A stack whose first 1x1 convolution has been applied to the SOURCE points (z = W0 . rows, an ordinary one-layer
-    stack): include/o3d_b200.h `o3d_lift_t`.  Inputs: z (rows, C0), ridx (P,) int32 | None, cc (P/grp, C0) | None,
-    s (P,) | None, u (C0,) | None; params as in _MLPStackFn with layer 0 = (None, None, gamma0, beta0)."""
+    """A stack whose first 1x1 convolution has been split (include/o3d_b200.h `o3d_lift_t`): its feature part applied to the
+    SOURCE points (z = W0_f . rows, an ordinary one-layer stack) and gathered, plus up to four per-position scalars s with
+    weight rows u.  Inputs: z (rows, C0) | None, ridx (P,) int32 | None, s (P, 4) | None, u (4, C0) | None; params as in
+    _MLPStackFn with layer 0 = (None, None, gamma0, beta0)."""
 
     @staticmethod
-    def forward(ctx, meta, geom, z, ridx, cc, s, u, *params):
-        P, C0 = geom.P, z.shape[1]
-        for t in (z, ridx, cc, s, u) + tuple(params):
+    def forward(ctx, meta, geom, c0, z, ridx, s, u, *params):
+        P, C0 = geom.P, c0
+        for t in (z, ridx, s, u) + tuple(params):
             if t is not None and not t.is_contiguous():
                 raise RuntimeError("lifted MLP stack: tensors must be contiguous")
+        dev = (z if z is not None else s).device
         d = _describe(meta, P, C0, params)
         lf = _lib.LiftDesc()
-        lf.z, lf.ldz, lf.ridx, lf.ridx_mod = z.data_ptr(), C0, _ptr(ridx), geom.ridx_mod
-        lf.rows_per_cloud, lf.pos_per_cloud, lf.cc, lf.grp = geom.rows_per_cloud, geom.pos_per_cloud, _ptr(cc), geom.grp
+        lf.z, lf.ldz, lf.ridx, lf.ridx_mod = _ptr(z), C0, _ptr(ridx), geom.ridx_mod
+        lf.rows_per_cloud, lf.pos_per_cloud, lf.grp = geom.rows_per_cloud, geom.pos_per_cloud, geom.grp
         lf.s, lf.u = _ptr(s), _ptr(u)
         d.lift = ctypes.pointer(lf)
         L = _lib.lib()
@@ -202,25 +204,25 @@ class _LiftedStackFn(torch.autograd.Function):
         nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 0)
         if nbytes < 0:
             raise RuntimeError("lifted MLP stack: invalid stack description")
-        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=z.device)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
         rows = P // meta.S if meta.S > 0 else P
         Nw, Cout = _r4(meta.cout[-1]), meta.cout[-1]
-        out = torch.empty(rows, Nw, dtype=torch.float32, device=z.device)
+        out = torch.empty(rows, Nw, dtype=torch.float32, device=dev)
         ops.LAUNCHES += 3 * meta.n + 1
         _lib.check(L.o3d_stack_forward(ctypes.byref(d), None, ws.data_ptr(), out.data_ptr(), int(need_grad), _stream()),
                    "o3d_stack_forward (lifted)")
         if need_grad:
             ctx.meta, ctx.geom, ctx.desc, ctx.lf, ctx.params = meta, geom, d, lf, params
-            ctx.save_for_backward(z, ridx, cc, s, u, ws, out)
+            ctx.save_for_backward(z, ridx, s, u, ws, out)
         return out if Nw == Cout else out[:, :Cout]
 
     @staticmethod
     def backward(ctx, dout):
         meta, geom, d, lf, params = ctx.meta, ctx.geom, ctx.desc, ctx.lf, ctx.params
-        z, ridx, cc, s, u, ws, out = ctx.saved_tensors
+        z, ridx, s, u, ws, out = ctx.saved_tensors
         Nw = out.shape[1]
         if dout.shape[1] != Nw or not dout.is_contiguous():
-            dpad = torch.zeros(out.shape, dtype=torch.float32, device=z.device)
+            dpad = torch.zeros(out.shape, dtype=torch.float32, device=out.device)
             dpad[:, :dout.shape[1]] = dout
             dout = dpad
         grads = [None] * (4 * meta.n)
@@ -235,28 +237,27 @@ class _LiftedStackFn(torch.autograd.Function):
                 else:
                     fields[j][l] = None
         need = ctx.needs_input_grad
-        dz = torch.zeros_like(z) if need[2] else None
-        dcc = torch.empty_like(cc) if (cc is not None and need[4]) else None
+        dz = torch.zeros_like(z) if (z is not None and need[3]) else None
         ds = torch.zeros_like(s) if (s is not None and need[5]) else None
         du = torch.zeros_like(u) if (u is not None and need[6]) else None
-        lf.d_z, lf.d_cc, lf.d_s, lf.d_u = _ptr(dz), _ptr(dcc), _ptr(ds), _ptr(du)
+        lf.d_z, lf.d_s, lf.d_u = _ptr(dz), _ptr(ds), _ptr(du)
         L = _lib.lib()
         nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 1)
-        wb = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=z.device)
+        wb = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=out.device)
         ops.LAUNCHES += 5 * meta.n + 1
         _lib.check(L.o3d_stack_backward(ctypes.byref(d), None, ws.data_ptr(), wb.data_ptr(), out.data_ptr(), dout.data_ptr(),
                                         None, _stream()), "o3d_stack_backward (lifted)")
-        return (None, None, dz, None, dcc, ds, du, *grads)
+        return (None, None, None, dz, None, ds, du, *grads)
 
 
-def lifted_stack(z, specs, geom, ridx=None, cc=None, s=None, u=None, S=0, training=True):
-    """specs[0] is the lifted layer: its conv has ALREADY been applied (that is `z`); only its BatchNorm / ReLU remain."""
-    first = _LayerSpec(None, None, specs[0].bn, specs[0].relu, lift_c0=z.shape[1])
+def lifted_stack(specs, geom, c0, z=None, ridx=None, s=None, u=None, S=0, training=True):
+    """specs[0] is the lifted layer: its conv has ALREADY been applied (z, s.u); only its BatchNorm / ReLU remain."""
+    first = _LayerSpec(None, None, specs[0].bn, specs[0].relu, lift_c0=c0)
     meta = _Meta([first] + list(specs[1:]), S, training)
     params = [None, None, first.bn.weight if first.bn is not None else None, first.bn.bias if first.bn is not None else None]
     for sp in specs[1:]:
         params += [sp.weight, sp.bias, sp.bn.weight if sp.bn is not None else None, sp.bn.bias if sp.bn is not None else None]
-    return _LiftedStackFn.apply(meta, geom, z, ridx, cc, s, u, *params)
+    return _LiftedStackFn.apply(meta, geom, c0, z, ridx, s, u, *params)
 
 
 def _pow2_divisor(n, cap=64):
@@ -266,9 +267,9 @@ def _pow2_divisor(n, cap=64):
     return g
 
 
-def _liftable(specs):
+def _liftable(specs, site=None, info=None):
     """The first conv can be lifted when another layer follows it, its output width is a multiple of 4, and lifting is on."""
-    return runtime.lift_enabled() and len(specs) >= 2 and specs[0].weight.shape[0] % 4 == 0
+    return runtime.lift_enabled(site, info) and len(specs) >= 2 and specs[0].weight.shape[0] % 4 == 0
 
 
 def mlp_stack(x2d, specs, S=0, training=True, xyz_first=False, c0=0, dx_cols=0):
@@ -339,23 +340,33 @@ def sa_forward(sa, xyz, features, sample_idxs):
         if not grouper.use_xyz:
             raise RuntimeError("fused SA layer expects use_xyz=True (every shipped model does)")
         need_xyz = torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad)
-        if _liftable(specs) and not grouper.normalize_xyz:
-            # Lifted first layer: W0 . [x(idx) - c, f(idx)] = (W0 . [x, f])[idx] - W0_xyz . c  — the convolution runs once per
-            # SOURCE point (z) and once per centre (cc); the grouped (B, 3+C, npoint, nsample) tensor never exists
-            # (pointnet2_utils.py:317-329 + the first SharedMLP layer, pointnet2_modules.py:64-69).
+        if _liftable(specs, "sa", {"N": N, "npoint": npoint, "S": S, "C": C}) and (specs[0].bias is None or feat_cl is not None):
+            # Lifted first layer: W0 . [x(idx) - c, f(idx)] = (W0_f . f)[idx] + W0_x . (x(idx) - c) — the feature part of the
+            # convolution runs once per SOURCE point (z) and is gathered; the relative coordinates (dx, dy, dz) are applied per
+            # position, directly (same difference-then-multiply arithmetic as the reference).  The grouped
+            # (B, 3+C, npoint, nsample) tensor never exists (pointnet2_utils.py:317-329 + the first SharedMLP layer,
+            # pointnet2_modules.py:64-69).
             W0 = specs[0].weight
             C0 = W0.shape[0]
-            if feat_cl is None:
-                rows = F.pad(xyz, (0, 1))                                               # (B, N, 4): [x y z 0]
-            else:
-                rows = torch.cat([feat_cl, xyz, xyz.new_zeros(B, N, 1)], dim=2)         # (B, N, Cp + 4): [features | x y z 0]
-            z = mlp_stack(rows.view(B * N, rows.shape[2]), [_LayerSpec(W0, specs[0].bias, None, False)], 0, sa.training,
-                          xyz_first=True, c0=C, dx_cols=0 if (need_xyz or Cp == 0) else Cp)
-            Wx = W0.reshape(C0, -1)[:, :3].contiguous()
-            cc = mlp_stack(F.pad(new_xyz, (0, 1)).view(B * npoint, 4), [_LayerSpec(Wx, None, None, False)], 0, sa.training)
-            idx = pointnet2_utils.ball_query(grouper.radius, S, xyz, new_xyz)            # (B, npoint, S) int32, non-differentiable
+            W2 = W0.reshape(C0, -1)
+            if runtime.CHOICE_HOOK is None:
+                # fused ball query + relative coordinates: grouped (B, npoint, S, 4) = [dx dy dz 0], idx (B, npoint, S)
+                rel, idx = pointnet2_utils.query_and_group_cl(xyz, new_xyz, None, grouper.radius, S, grouper.normalize_xyz)
+            else:   # parity tests: record / substitute the discrete choice, relative coordinates by plain indexing
+                idx = runtime.choose("ball_query", {"radius": grouper.radius, "nsample": S, "N": N, "npoint": npoint},
+                                     lambda: pointnet2_utils.ball_query(grouper.radius, S, xyz, new_xyz))
+                rel = xyz.gather(1, idx.long().view(B, -1, 1).expand(-1, -1, 3)).view(B, npoint, S, 3) - new_xyz.unsqueeze(2)
+                if grouper.normalize_xyz:
+                    rel = rel / grouper.radius
+                rel = F.pad(rel, (0, 1)).contiguous()
+            u = F.pad(W2[:, :3].t(), (0, 0, 0, 1)).contiguous()                          # (4, C0): rows = W0's xyz columns, 0
+            z = None
+            if feat_cl is not None:
+                z = mlp_stack(feat_cl.view(B * N, Cp), [_LayerSpec(W2[:, 3:].contiguous(), specs[0].bias, None, False)], 0,
+                              sa.training)
             geom = _LiftGeom(B * npoint * S, 0, N, npoint * S, S)
-            pooled = lifted_stack(z, specs, geom, ridx=idx.view(-1), cc=cc, S=S, training=sa.training)
+            pooled = lifted_stack(specs, geom, C0, z=z, ridx=idx.view(-1) if z is not None else None,
+                                  s=rel.view(B * npoint * S, 4), u=u, S=S, training=sa.training)
         else:
             grouped, _idx = pointnet2_utils.query_and_group_cl(xyz, new_xyz, feat_cl, grouper.radius, S,
                                                                grouper.normalize_xyz)
@@ -422,6 +433,23 @@ class _GroupRowsCL(torch.autograd.Function):
         return gf, None
 
 
+class _P2BCosine(torch.autograd.Function):
+    """nn.CosineSimilarity(dim=1) between every (template, search) feature pair (xcorr.py:37-38) -> (B, n2, n1)."""
+
+    @staticmethod
+    def forward(ctx, t_cl, s_cl):
+        sim, tn, sn = ops.p2b_cosine(t_cl, s_cl)
+        ctx.save_for_backward(t_cl, s_cl, sim, tn, sn)
+        return sim
+
+    @staticmethod
+    def backward(ctx, dsim):
+        t_cl, s_cl, sim, tn, sn = ctx.saved_tensors
+        dt, ds = ops.p2b_cosine_grad(dsim.contiguous(), sim, t_cl, s_cl, tn, sn, need_t=ctx.needs_input_grad[0],
+                                     need_s=ctx.needs_input_grad[1])
+        return dt, ds
+
+
 def boxaware_xcorr_forward(xc, template_feature, search_feature, template_xyz, template_bc, search_bc):
     """Fused BoxAwareXCorr.forward (models/head/xcorr.py:81-103): box-cloud top-k, row gather, MLP + max over k."""
     B, f, M = template_feature.shape
@@ -429,20 +457,21 @@ def boxaware_xcorr_forward(xc, template_feature, search_feature, template_xyz, t
     k = xc.k
     if 128 % k != 0:
         raise RuntimeError(f"fused BoxAwareXCorr: k={k} must divide 128")
-    dist = torch.cdist(template_bc, search_bc)                                        # same formulation as the reference
-    topk = torch.argsort(dist, dim=1, stable=True)[:, :k, :].transpose(1, 2).contiguous().int()   # (B,N,k)
+    # (B,N,k) nearest template box clouds per search point: o3d_xcorr_boxaware_fwd (the reference: cdist + argsort[:k])
+    topk = runtime.choose("boxaware_topk", {"k": k, "M": M, "N": N},
+                          lambda: ops.boxaware_topk(template_bc.detach().contiguous(), search_bc.detach().contiguous(), k))
     # channel order [xyz(3), bc(9), feat(f)] == the reference's cat order (xcorr.py:82-84)
     tmpl = torch.cat([template_xyz, template_bc, template_feature.transpose(1, 2)], dim=2)
     C = tmpl.shape[2]
     if C % 4:
         tmpl = F.pad(tmpl, (0, _r4(C) - C))
     specs = parse_stack(xc.mlp)
-    if _liftable(specs) and (N * k) % 4 == 0:
+    if _liftable(specs, "bax") and (N * k) % 4 == 0:
         # lifted: the first conv runs on the M template rows; the (B, 268, N, k) grouped tensor is never built (xcorr.py:89-98)
         tm = tmpl.contiguous()
         z = mlp_stack(tm.view(B * M, tm.shape[2]), [_LayerSpec(specs[0].weight, specs[0].bias, None, False)], 0, xc.training)
         geom = _LiftGeom(B * N * k, 0, M, N * k, _pow2_divisor(N * k))
-        pooled = lifted_stack(z, specs, geom, ridx=topk.view(-1), S=k, training=xc.training)
+        pooled = lifted_stack(specs, geom, z.shape[1], z=z, ridx=topk.view(-1), S=k, training=xc.training)
     else:
         rows = _GroupRowsCL.apply(tmpl.contiguous(), topk.view(B, N * k))                 # (B, N*k, Cp)
         pooled = mlp_stack(rows.view(B * N * k, rows.shape[2]), specs, k, xc.training)
@@ -457,10 +486,11 @@ def p2b_xcorr_forward(xc, template_feature, search_feature, template_xyz):
     n2 = search_feature.shape[2]
     if 128 % n1 != 0:
         raise RuntimeError(f"fused P2B_XCorr: number of template points {n1} must divide 128")
-    sim = F.cosine_similarity(template_feature.unsqueeze(-1), search_feature.unsqueeze(2), dim=1)   # (B,n1,n2), eps 1e-8
     t_cl = template_feature.transpose(1, 2)                                                        # (B,n1,f)
+    sim_t = _P2BCosine.apply(t_cl.contiguous(), search_feature.transpose(1, 2).contiguous())       # (B,n2,n1), eps 1e-8
+    sim = sim_t.transpose(1, 2)                                                                    # (B,n1,n2) as the reference
     specs = parse_stack(xc.mlp)
-    if _liftable(specs) and (n1 & (n1 - 1)) == 0:
+    if _liftable(specs, "p2b") and (n1 & (n1 - 1)) == 0:
         # lifted: the first conv's input [sim(1), xyz(3), feature(f)] (xcorr.py:39-46) is a per-template row plus ONE scalar
         # per (search, template) pair, so Y0[(b,j,i)] = (W[:,1:] . [xyz_i, f_i]) + sim[b,i,j] * W[:,0] and the
         # (B, 260, n1, n2) fusion tensor is never built
@@ -472,8 +502,8 @@ def p2b_xcorr_forward(xc, template_feature, search_feature, template_xyz):
         z = mlp_stack(rows.reshape(B * n1, rows.shape[2]), [_LayerSpec(W0[:, 1:].contiguous(), specs[0].bias, None, False)], 0,
                       xc.training)
         geom = _LiftGeom(B * n2 * n1, n1, n1, n2 * n1, n1)
-        pooled = lifted_stack(z, specs, geom, s=sim.transpose(1, 2).reshape(-1), u=W0[:, 0].contiguous(), S=n1,
-                              training=xc.training)
+        pooled = lifted_stack(specs, geom, z.shape[1], z=z, s=F.pad(sim_t.reshape(-1, 1), (0, 3)),
+                              u=F.pad(W0[:, :1].t(), (0, 0, 0, 3)).contiguous(), S=n1, training=xc.training)
     else:
         fusion = torch.cat([sim.transpose(1, 2).unsqueeze(-1),                                      # (B,n2,n1,1)
                             template_xyz.unsqueeze(1).expand(B, n2, n1, 3),

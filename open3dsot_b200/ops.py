@@ -176,6 +176,42 @@ def three_nn_interpolate_grad(grad_out_cl, idx, weight, m):
     return g
 
 
+# ------------------------------------------------------------------ cross-correlation front ends (models/head/xcorr.py)
+def boxaware_topk(template_bc, search_bc, k):
+    """template_bc (B,M,D), search_bc (B,N,D) -> idx (B,N,k) int32: nearest template box clouds per search point."""
+    _chk_f(template_bc, "template_bc"); _chk_f(search_bc, "search_bc")
+    B, M, D = template_bc.shape
+    N = search_bc.shape[1]
+    idx = torch.empty(B, N, int(k), dtype=torch.int32, device=search_bc.device)
+    _call("o3d_xcorr_boxaware_fwd", template_bc.data_ptr(), search_bc.data_ptr(), B, M, N, D, int(k), idx.data_ptr(), _stream())
+    return idx
+
+
+def p2b_cosine(tfeat_cl, sfeat_cl, eps=1e-8):
+    """tfeat_cl (B,n1,C), sfeat_cl (B,n2,C) -> sim (B,n2,n1), tnorm (B,n1), snorm (B,n2)."""
+    _chk_f(tfeat_cl, "tfeat_cl"); _chk_f(sfeat_cl, "sfeat_cl")
+    B, n1, C = tfeat_cl.shape
+    n2 = sfeat_cl.shape[1]
+    dev = tfeat_cl.device
+    sim = torch.empty(B, n2, n1, dtype=torch.float32, device=dev)
+    tn = torch.empty(B, n1, dtype=torch.float32, device=dev)
+    sn = torch.empty(B, n2, dtype=torch.float32, device=dev)
+    _call("o3d_xcorr_p2b_fwd", tfeat_cl.data_ptr(), sfeat_cl.data_ptr(), B, n1, n2, C, float(eps), sim.data_ptr(), tn.data_ptr(),
+          sn.data_ptr(), _stream())
+    return sim, tn, sn
+
+
+def p2b_cosine_grad(dsim, sim, tfeat_cl, sfeat_cl, tn, sn, eps=1e-8, need_t=True, need_s=True):
+    _chk_f(dsim, "dsim")
+    B, n1, C = tfeat_cl.shape
+    n2 = sfeat_cl.shape[1]
+    dt = torch.empty_like(tfeat_cl) if need_t else None
+    dsf = torch.empty_like(sfeat_cl) if need_s else None
+    _call("o3d_xcorr_p2b_bwd", dsim.data_ptr(), sim.data_ptr(), tfeat_cl.data_ptr(), sfeat_cl.data_ptr(), tn.data_ptr(),
+          sn.data_ptr(), B, n1, n2, C, float(eps), dt.data_ptr() if need_t else None, dsf.data_ptr() if need_s else None, _stream())
+    return dt, dsf
+
+
 # ------------------------------------------------------------------ box-frame crop (tracking loop / training sampler)
 def crop_box_frame(scans, center, rot, half, frame=None, count=None):
     """scans (F, N, 3) fp32 CUDA; center (B, 3), rot (B, 3, 3), half (B, 3); frame (B,) int64 picks a scan per sample

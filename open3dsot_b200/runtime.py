@@ -14,8 +14,15 @@ _TC = int(os.environ.get("O3D_TC", "3"))
 _LIFT = os.environ.get("O3D_LIFT", "1") != "0"
 
 
-def lift_enabled() -> bool:
-    return _LIFT
+LIFT_FILTER = None      # diagnostics: callable(site: str, info: dict) -> bool restricting which stacks are lifted
+
+
+def lift_enabled(site=None, info=None) -> bool:
+    if not _LIFT:
+        return False
+    if LIFT_FILTER is not None and site is not None:
+        return bool(LIFT_FILTER(site, info or {}))
+    return True
 
 
 def set_lift(flag: bool) -> None:
@@ -55,3 +62,20 @@ def composed_mode():
         yield
     finally:
         _FUSED = old
+
+
+# ---- discrete-choice hook (parity tests only) -------------------------------------------------------------------
+# The forward pass takes three kinds of data-dependent DISCRETE decisions on computed values: the ball query of every
+# set-abstraction layer (on input coordinates in the backbone, on VOTED coordinates in the RPN), and BoxAwareXCorr's top-k
+# over predicted box clouds.  A neighbour that sits within fp32 round-off of the radius / of the k-th distance can fall the
+# other way on the GPU than in the CPU oracle, which changes downstream floats by O(1e-3) without any kernel being wrong.
+# Parity tests install a hook that (a) records the product's own choice and (b) may substitute the oracle's, so that the
+# float path is compared at 1e-4 with identical discrete choices.  hook(kind, info, compute) -> int32 tensor; `compute()`
+# evaluates the product's choice.  None (the default) = no hook: the product path is unchanged.
+CHOICE_HOOK = None
+
+
+def choose(kind, info, compute):
+    if CHOICE_HOOK is None:
+        return compute()
+    return CHOICE_HOOK(kind, info, compute)

@@ -15,6 +15,37 @@ from . import ops
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
+# Optional recorder of intermediates (tests): set to a dict; every call appends to TAPS[name] in call order
+# (the shared backbone runs on the template first, then on the search area: bat.py:89-90).
+TAPS = None
+
+
+# Optional substitution of the DISCRETE choices (ball-query indices, box-cloud top-k), by kind and call order: the parity tests
+# run the oracle a second time in float64 (the "exact" arithmetic) with the float32 run's choices, so that the two runs differ by
+# floating-point round-off only.  FORCE = {"ball_query": [idx, ...], "topk": [idx]}; None = compute.
+FORCE = None
+_calls = {}
+
+
+def _choice(kind, compute):
+    if FORCE is None:
+        return compute()
+    n = _calls.get(kind, 0)
+    _calls[kind] = n + 1
+    forced = FORCE.get(kind, [])
+    return forced[n] if n < len(forced) and forced[n] is not None else compute()
+
+
+def set_force(force):
+    global FORCE
+    FORCE = force
+    _calls.clear()
+
+
+def _tap(name, value):
+    if TAPS is not None:
+        TAPS.setdefault(name, []).append(value.detach().clone() if torch.is_tensor(value) else value)
+
 
 # --------------------------------------------------------------------------- index helpers
 def gather_cols(features, idx):
@@ -87,7 +118,8 @@ def seq_conv1d(x, sd, prefix, training, last_has_activation=False):
 # --------------------------------------------------------------------------- PointNet++ layers
 def query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True, normalize_xyz=False):
     """QueryAndGroup.forward (pointnet2/utils/pointnet2_utils.py:299-339)."""
-    idx = ops.ball_query(new_xyz.detach().contiguous(), xyz.detach().contiguous(), radius, nsample)
+    idx = _choice("ball_query", lambda: ops.ball_query(new_xyz.detach().float().contiguous(), xyz.detach().float().contiguous(),
+                                                      radius, nsample))
     grouped_xyz = group_cols(xyz.transpose(1, 2), idx) - new_xyz.transpose(1, 2).unsqueeze(-1)
     if normalize_xyz:
         grouped_xyz = grouped_xyz / radius
@@ -106,13 +138,15 @@ def sa_module(sd, prefix, xyz, features, npoint, radius, nsample, use_fps, train
     FPS or the first `npoint` points as centres -> group -> SharedMLP -> max over nsample."""
     B = xyz.shape[0]
     if use_fps:
-        sample_idxs = ops.furthest_point_sampling(xyz.detach().contiguous(), npoint)
+        sample_idxs = ops.furthest_point_sampling(xyz.detach().float().contiguous(), npoint)
     else:
         sample_idxs = torch.arange(npoint, dtype=torch.int32).repeat(B, 1)
     new_xyz = gather_cols(xyz.transpose(1, 2), sample_idxs).transpose(1, 2).contiguous()
-    grouped, _ = query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz, normalize_xyz)
+    grouped, bq_idx = query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz, normalize_xyz)
     y = shared_mlp(grouped, sd, f"{prefix}.mlps.0", training)
     y = F.max_pool2d(y, kernel_size=[1, y.size(3)]).squeeze(-1)
+    _tap(f"{prefix}:bq_idx", bq_idx)
+    _tap(f"{prefix}:out", y)
     return new_xyz, y, sample_idxs
 
 
@@ -151,13 +185,16 @@ def boxaware_xcorr(sd, prefix, t_feat, s_feat, t_xyz, s_xyz, t_bc, s_bc, k, trai
     """BoxAwareXCorr.forward (models/head/xcorr.py:67-103) with use_search_bc/use_search_feature False
     (the only setting any shipped cfg uses; the other branches reference an undefined `self.K`)."""
     dist = torch.cdist(t_bc, s_bc)  # (B,M,N), matmul formulation for these sizes
-    topk = torch.argsort(dist, dim=1, stable=True)[:, :k, :]  # reference: unstable argsort (ties undefined)
-    topk = topk.transpose(1, 2).contiguous().int()  # (B,N,k)
+    topk = _choice("topk", lambda: torch.argsort(dist, dim=1, stable=True)[:, :k, :]   # reference: unstable argsort (ties undefined)
+                   .transpose(1, 2).contiguous().int())  # (B,N,k)
     tmpl = torch.cat([t_xyz.transpose(1, 2), t_bc.transpose(1, 2), t_feat], dim=1)
     corr = group_cols(tmpl, topk)  # (B,3+9+D,N,k)
     y = shared_mlp(corr, sd, f"{prefix}.mlp", training)
     y = y.max(dim=-1)[0]
-    return seq_conv1d(y, sd, f"{prefix}.fea_layer", training), topk
+    out = seq_conv1d(y, sd, f"{prefix}.fea_layer", training)
+    _tap(f"{prefix}:topk", topk)
+    _tap(f"{prefix}:out", out)
+    return out, topk
 
 
 def p2b_xcorr(sd, prefix, t_feat, s_feat, t_xyz, training):
@@ -171,7 +208,9 @@ def p2b_xcorr(sd, prefix, t_feat, s_feat, t_xyz, training):
                         t_feat.unsqueeze(-1).expand(B, f, n1, n2)], dim=1)
     y = shared_mlp(fusion, sd, f"{prefix}.mlp", training)
     y = F.max_pool2d(y, kernel_size=[y.size(2), 1]).squeeze(2)
-    return seq_conv1d(y, sd, f"{prefix}.fea_layer", training)
+    out = seq_conv1d(y, sd, f"{prefix}.fea_layer", training)
+    _tap(f"{prefix}:out", out)
+    return out
 
 
 def rpn(sd, prefix, xyz, feature, num_proposal, training, normalize_xyz=False):
