@@ -1,9 +1,12 @@
 """CPU oracle (TEST INFRASTRUCTURE ONLY) for the B=1 tracking-inference path of SURVEY.md §8(f) rank 2: the geometry the
 reference's frame loop runs on the host between two model calls.
 
-PARITY UNPINNED: the reference functions live in datasets/points_utils.py / datasets/data_classes.py / utils/metrics.py and
-need pyquaternion, shapely, nuscenes-devkit and torchmetrics, none of which is installed here, so they cannot be executed
-to produce golden vectors.  This file restates their arithmetic with plain numpy, one function per reference function, each
+PINNED (round 2) for the geometry: tests/golden/make_golden_tracking.py runs the reference's own, unmodified
+datasets/points_utils.py / data_classes.py / sampler.py (with numpy stand-ins for pyquaternion and nuscenes-devkit's
+points_in_box, tests/golden/_ref_shims.py) and commits its outputs; tests/test_tracking_golden.py holds every geometry function
+here and the whole `siamese_processing` to them at 1e-9 / 1e-5 on the recorded random draws.  Still unpinned: the metrics
+(utils/metrics.py needs shapely / torchmetrics) and the motion-centric `motion_processing`.
+This file restates the reference arithmetic with plain numpy, one function per reference function, each
 citing the lines it follows; orientations are carried as 3x3 rotation matrices (pyquaternion is only used upstream to
 compose and invert rotations: `Quaternion(matrix=M)` == M, `.inverse` == M.T, `q1 * q2` == M1 @ M2,
 `Quaternion(axis=[0,0,1], degrees=a)` == rotz(a)), and polygon clipping replaces shapely for the two convex
