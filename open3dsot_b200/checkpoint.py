@@ -78,3 +78,47 @@ def load_reference_weights(model, path, strict=True, map_location="cpu"):
     sd = {k: v for k, v in ckpt["state_dict"].items()}
     model.load_state_dict(sd, strict=strict)
     return ckpt
+
+
+def save_lightning_checkpoint(model, path, epoch=0, global_step=0, optimizer_states=None, lr_schedulers=None, extra_state_dict=None):
+    """Write `model` in the layout of the reference's Lightning-1.3.8 checkpoints, so that the reference's
+    own `Model.load_from_checkpoint(path, config=cfg)` / `--checkpoint` (main.py:67-70,78-79) reads it back:
+
+        state_dict                 parameter / buffer names exactly as the reference's modules name them
+        hyper_parameters           {"config": EasyDict(...)} — pickled under the global name `easydict.EasyDict`
+        epoch, global_step, pytorch-lightning_version ("1.3.8"), optimizer_states, lr_schedulers, callbacks
+
+    `extra_state_dict`: entries of the reference's parameter-free metric modules (`prec.*`, `success.*`: torchmetrics buffers)
+    to carry over from a loaded checkpoint; they hold no weights and are absent by default (Lightning loads non-strictly
+    only if asked, so pass them through when the file must load with `strict=True` in the reference)."""
+    import sys
+    import types
+    from .compat import easydict as _ed
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    if extra_state_dict:
+        sd.update({k: v.detach().cpu().clone() for k, v in extra_state_dict.items()})
+    cfg = getattr(model, "config", None)
+    hp = dict(getattr(model, "hparams", {}) or {})
+    if cfg is not None:
+        hp["config"] = _ed.EasyDict(dict(cfg))
+    ckpt = {"epoch": int(epoch), "global_step": int(global_step), "pytorch-lightning_version": "1.3.8", "state_dict": sd,
+            "hyper_parameters": hp, "optimizer_states": optimizer_states or [], "lr_schedulers": lr_schedulers or [], "callbacks": {}}
+    # the stand-in EasyDict must be written under the name the reference environment resolves: easydict.EasyDict
+    cls = _ed.EasyDict
+    shim = None
+    if cls.__module__ != "easydict":
+        shim = types.ModuleType("easydict")
+        shim.EasyDict = cls
+        old = (cls.__module__, cls.__qualname__, sys.modules.get("easydict"))
+        cls.__module__, cls.__qualname__ = "easydict", "EasyDict"
+        sys.modules["easydict"] = shim
+    try:
+        torch.save(ckpt, path, _use_new_zipfile_serialization=False)      # the legacy (non-zip) format Lightning 1.3.8 wrote
+    finally:
+        if shim is not None:
+            cls.__module__, cls.__qualname__ = old[0], old[1]
+            if old[2] is None:
+                sys.modules.pop("easydict", None)
+            else:
+                sys.modules["easydict"] = old[2]
+    return path

@@ -237,6 +237,27 @@ def gen_m2track(out):
     out["m2_eval_boxes"] = np_(ep["estimation_boxes"])
 
 
+def gen_checkpoint_eval(out):
+    """the reference's shipped `pretrained_models/bat_kitti_car.ckpt` through the reference's own BAT in
+    eval mode on a fixed synthetic pair -> outputs (committed) + the state dict as a plain npz under tests/golden/_ckpt/
+    (git-ignored: trained weights are not source; the GPU box receives the file with the working tree)."""
+    from models import get_model
+    from open3dsot_b200.checkpoint import load_lightning_checkpoint
+    ck = load_lightning_checkpoint(os.path.join(REF, "pretrained_models", "bat_kitti_car.ckpt"))
+    cfg = EasyDict(load_yaml(os.path.join(ROOT, "cfgs", "BAT_Car.yaml")))
+    net = get_model(cfg.net_model)(cfg)
+    missing = net.load_state_dict(ck["state_dict"], strict=False)
+    assert not [k for k in missing.missing_keys if not k.split(".")[0] in ("prec", "success")], missing
+    net.eval()
+    batch = synthetic_siamese_batch(2, 512, 1024, seed=4242, box_aware=True)
+    with torch.no_grad():
+        ep = net({k: v.clone() for k, v in batch.items()})
+    for k in ("estimation_boxes", "estimation_cla", "vote_xyz", "center_xyz", "sample_idxs", "pred_search_bc"):
+        out[f"ckpt_bat_car_{k}"] = np_(ep[k])
+    os.makedirs(os.path.join(HERE, "_ckpt"), exist_ok=True)
+    np.savez(os.path.join(HERE, "_ckpt", "bat_kitti_car_state.npz"), **{k: np_(v) for k, v in ck["state_dict"].items()})
+
+
 def main():
     assert os.path.isdir(REF), "golden vectors can only be generated where /root/reference exists"
     install_stubs()
@@ -248,6 +269,7 @@ def main():
     gen_model("bat", "BAT_Car.yaml", 2, 256, 512, models, seed=21)
     gen_model("p2b", "P2B_Car.yaml", 2, 256, 512, models, seed=22)   # BASELINE.json configs[0] shape; B=2 (B=1 is a degenerate BatchNorm case)
     gen_m2track(models)
+    gen_checkpoint_eval(models)
     np.savez_compressed(os.path.join(HERE, "ref_models.npz"), **models)
     for f in ("ref_modules.npz", "ref_models.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

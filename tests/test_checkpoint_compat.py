@@ -65,3 +65,26 @@ def test_restricted_unpickler_neutralises_foreign_globals(tmp_path):
         assert cls is not getattr(builtins, name, None)
     assert _RestrictedUnpickler(io.BytesIO(b"")).find_class("collections", "OrderedDict").__name__ == "OrderedDict"
     pickle.dumps(1)
+
+
+def test_save_checkpoint_round_trips_in_the_reference_layout(tmp_path):
+    """`save_lightning_checkpoint` writes the §8b layout: the reference's key names, `hyper_parameters.config` pickled as
+    `easydict.EasyDict` (no trace of this package in the file), Lightning's bookkeeping keys; reading it back is lossless."""
+    from open3dsot_b200.checkpoint import save_lightning_checkpoint
+    cfg = load_config(os.path.join(ROOT, "cfgs", "BAT_Car.yaml"))
+    net = get_model(cfg.net_model)(cfg)
+    load_reference_weights(net, os.path.join(CKPT_DIR, "bat_kitti_car.ckpt"), strict=False)
+    path = str(tmp_path / "ours.ckpt")
+    save_lightning_checkpoint(net, path, epoch=7, global_step=1234)
+    raw = open(path, "rb").read()
+    assert b"easydict" in raw and b"open3dsot_b200" not in raw
+    ck = load_lightning_checkpoint(path)
+    ref = load_lightning_checkpoint(os.path.join(CKPT_DIR, "bat_kitti_car.ckpt"))
+    assert set(ref.keys()) - set(ck.keys()) <= {"hparams_name"}
+    assert ck["epoch"] == 7 and ck["global_step"] == 1234 and ck["pytorch-lightning_version"] == "1.3.8"
+    assert ck["hyper_parameters"]["config"].net_model == "BAT" and ck["hyper_parameters"]["config"].use_fps is True
+    assert list(ck["state_dict"].keys()) == [k for k in ref["state_dict"].keys() if k in ck["state_dict"]]   # same names, same order
+    for k, v in ck["state_dict"].items():
+        assert torch.equal(v, ref["state_dict"][k]), k
+    net2 = get_model(cfg.net_model)(cfg)
+    load_reference_weights(net2, path, strict=True)
