@@ -215,6 +215,28 @@ def run_track(args):
         res[name + "_fps"] = n / max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
         res[name + "_ms_device"] = e0.elapsed_time(e1) / n
     clocks = sampler.stop()
+    if args.kernel_table:                       # per-kernel device time of eager device frames (CUPTI)
+        from torch.profiler import ProfilerActivity, profile
+        trk = DeviceTracker(net, max_points=npts, use_graph=False)
+        trk.reset(pts[0], seq[0]["3d_bbox"].to_tensor(dev))
+        for i in range(1, 4):
+            trk.step(pts[i])
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(4, 7):
+                trk.step(pts[i])
+            torch.cuda.synchronize()
+        agg = {}
+        for e in prof.events():
+            if e.device_type.name == "CUDA":
+                a = agg.setdefault(e.name, [0, 0.0])
+                a[0] += 1
+                a[1] += e.device_time
+        tot = sum(v[1] for v in agg.values())
+        with open(args.kernel_table, "w") as f:
+            f.write(f"# CUPTI kernel activity, 3 eager tracking frames; {sum(v[0] for v in agg.values()) / 3:.0f} launches, {tot / 3:.1f} us of kernel time per frame\n")
+            for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"{100 * us / tot:7.2f}% {us / 3:9.1f} us {n / 3:7.1f}  {name[:140]}\n")
     cb = None if args.no_cpu_baseline else track_cpu_baseline(cfg, seq, 8)
     print(json.dumps({"metric": f"tracking frames/sec, {cfg.net_model} B=1 (crop + resample + network + box update per frame)",
                       "value": res["device_graph_fps"], "unit": "frames/s", "n_gpus": 1, "steps": frames - w - 1, "warmup": w,

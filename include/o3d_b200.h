@@ -265,9 +265,14 @@ typedef struct o3d_stack_t {
     float* d_gamma[O3D_MAX_LAYERS];
     float* d_beta[O3D_MAX_LAYERS];
     const o3d_lift_t* lift;   /* non-NULL: layer 0 is lifted (weight[0] == NULL, cout[0] = C0, K0 = round4(C0), x unused) */
+    const void* prepared;     /* non-NULL (inference only): parameter block filled by o3d_stack_prepare(); the forward then
+                                 neither packs weights nor finalises BatchNorm                                            */
 } o3d_stack_t;
 
 long long o3d_stack_workspace_bytes(const o3d_stack_t* d, int backward);
+/* Static-weight inference (the B=1 tracking loop): pack the weights / fold the running BN statistics once. */
+long long o3d_stack_prepared_bytes(const o3d_stack_t* d);
+int o3d_stack_prepare(const o3d_stack_t* d, void* block, void* stream);
 /* out: [P or P/S, round4(cout_last)]; ws_fwd must stay alive (untouched) until the backward call. */
 int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float* out, int keep_for_backward,
                       void* stream);

@@ -69,11 +69,13 @@ PROTOTYPES = {
     "o3d_pw_wgrad_tc_lift": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p,
                              ctypes.c_longlong, _p],
     "o3d_stack_workspace_bytes": [_p, _i],
+    "o3d_stack_prepared_bytes": [_p],
+    "o3d_stack_prepare": [_p, _p, _p],
     "o3d_stack_forward": [_p, _p, _p, _p, _i, _p],
     "o3d_stack_backward": [_p, _p, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPE = {"o3d_last_error": ctypes.c_char_p, "o3d_pw_tc_wtile_bytes": ctypes.c_longlong,
-            "o3d_stack_workspace_bytes": ctypes.c_longlong, "o3d_debug_set": None, "o3d_pw_tc_set_reverse": None,
+            "o3d_stack_workspace_bytes": ctypes.c_longlong, "o3d_stack_prepared_bytes": ctypes.c_longlong, "o3d_debug_set": None, "o3d_pw_tc_set_reverse": None,
             "o3d_pw_wgrad_tc2_workspace_floats": ctypes.c_longlong}
 
 MAX_LAYERS = 8
@@ -96,7 +98,7 @@ class StackDesc(ctypes.Structure):
                 ("weight", _P8), ("bias", _P8), ("gamma", _P8), ("beta", _P8),
                 ("running_mean", _P8), ("running_var", _P8), ("num_batches_tracked", _P8),
                 ("d_weight", _P8), ("d_bias", _P8), ("d_gamma", _P8), ("d_beta", _P8),
-                ("lift", ctypes.POINTER(LiftDesc))]
+                ("lift", ctypes.POINTER(LiftDesc)), ("prepared", _p)]
 
 _lib = None
 

@@ -22,6 +22,8 @@
 #include "common.cuh"
 #include "../../include/o3d_b200.h"
 
+int o3d_g_fps_wide = 0;     // experiment switch (o3d_debug_set bit 10): twice the threads, half the points per thread
+
 namespace {
 
 struct FpsParams {
@@ -38,7 +40,7 @@ __device__ __forceinline__ uint32_t fps_bitrev(uint32_t t, int log2_block) {
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS) fps_kernel(const float* __restrict__ xyz, int32_t* __restrict__ idx,
                                                       FpsParams prm) {
-    extern __shared__ __align__(16) float s_xyz[];  // 3*N floats
+    extern __shared__ __align__(16) float s_xyz[];  // 3*N floats, then block_ref*cnt uint16: priority -> point index
     constexpr int NW = THREADS / 32;
     __shared__ uint32_t s_key[2][NW];
     __shared__ uint32_t s_pri[2][NW];
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(const float* __restrict__ 
     const float* __restrict__ p = xyz + (size_t)blockIdx.x * N * 3;
     int32_t* __restrict__ out = idx + (size_t)blockIdx.x * npoint;
 
+    uint16_t* s_dec = reinterpret_cast<uint16_t*>(s_xyz + 3 * N);   // decode table: a winner's priority -> its index (one LDS instead
+                                                                   // of a runtime integer division + modulo + bit reversal per iteration)
     for (int i = tid; i < 3 * N; i += THREADS) s_xyz[i] = p[i];
     __syncthreads();
 
@@ -64,31 +68,41 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(const float* __restrict__ 
             py[i] = s_xyz[k * 3 + 1];
             pz[i] = s_xyz[k * 3 + 2];
             const float mag = o3d_sq3(px[i], py[i], pz[i]);
-            if (!((double)mag <= 1e-3))
+            if (!((double)mag <= 1e-3)) {
                 pri[i] = fps_bitrev((uint32_t)(k % prm.block_ref), prm.log2_block) * (uint32_t)prm.cnt +
                          (uint32_t)(k / prm.block_ref);
+                s_dec[pri[i]] = (uint16_t)k;        // N <= 16384; priorities of eligible points are distinct and < block_ref * cnt
+            }
         }
     }
+    __syncthreads();
 
     int old = 0;
     if (tid == 0) out[0] = 0;
 
     for (int j = 1; j < npoint; ++j) {
         const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
-        uint32_t bk = 0u, bp = 0xFFFFFFFFu;  // key 0 == "no candidate" (upstream: best = -1, besti = 0)
+        // per-point keys first (independent), then a pairwise tournament: the dependent compare chain is log2(PPT) deep
+        uint32_t ck[PPT], cp[PPT];  // key 0 == "no candidate" (upstream: best = -1, besti = 0)
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
-            if (pri[i] != 0xFFFFFFFFu) {
-                const float d = o3d_dist2(px[i], py[i], pz[i], x1, y1, z1);
-                const float d2 = fminf(d, td[i]);
-                td[i] = d2;
-                const uint32_t key = __float_as_uint(d2) + 1u;  // d2 >= +0 -> bit pattern is monotone
-                if (key > bk || (key == bk && pri[i] < bp)) {
-                    bk = key;
-                    bp = pri[i];
-                }
+            const float d = o3d_dist2(px[i], py[i], pz[i], x1, y1, z1);
+            const float d2 = fminf(d, td[i]);
+            const bool live = pri[i] != 0xFFFFFFFFu;
+            td[i] = live ? d2 : td[i];
+            ck[i] = live ? __float_as_uint(d2) + 1u : 0u;  // d2 >= +0 -> bit pattern is monotone
+            cp[i] = pri[i];
+        }
+#pragma unroll
+        for (int w = 1; w < PPT; w <<= 1) {
+#pragma unroll
+            for (int i = 0; i + w < PPT; i += 2 * w) {
+                const bool take = ck[i + w] > ck[i] || (ck[i + w] == ck[i] && cp[i + w] < cp[i]);
+                ck[i] = take ? ck[i + w] : ck[i];
+                cp[i] = take ? cp[i + w] : cp[i];
             }
         }
+        const uint32_t bk = ck[0], bp = cp[0];
         const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, bk);
         const uint32_t wp = __reduce_min_sync(0xFFFFFFFFu, bk == wm ? bp : 0xFFFFFFFFu);
         const int buf = j & 1;
@@ -101,19 +115,14 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(const float* __restrict__ 
         const uint32_t p2 = lane < NW ? s_pri[buf][lane] : 0xFFFFFFFFu;
         const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, k2);
         const uint32_t q2 = __reduce_min_sync(0xFFFFFFFFu, k2 == m2 ? p2 : 0xFFFFFFFFu);
-        if (m2 == 0u) {
-            old = 0;
-        } else {
-            const uint32_t t = fps_bitrev(q2 / (uint32_t)prm.cnt, prm.log2_block);
-            old = (int)((q2 % (uint32_t)prm.cnt) * (uint32_t)prm.block_ref + t);
-        }
+        old = m2 == 0u ? 0 : (int)s_dec[q2];
         if (tid == 0) out[j] = old;
     }
 }
 
 template <int THREADS, int PPT>
 int launch_fps(const float* xyz, int B, int32_t* idx, const FpsParams& prm, cudaStream_t st) {
-    const size_t smem = (size_t)prm.N * 3 * sizeof(float);
+    const size_t smem = (size_t)prm.N * 3 * sizeof(float) + (size_t)prm.block_ref * prm.cnt * sizeof(uint16_t);
     if (smem > 48 * 1024)
         O3D_CUDA(cudaFuncSetAttribute(fps_kernel<THREADS, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "o3d_fps: smem attribute");
@@ -137,10 +146,14 @@ extern "C" int o3d_fps(const float* xyz, int B, int N, int npoint, int32_t* idx,
     while ((1 << prm.log2_block) < prm.block_ref) ++prm.log2_block;
     prm.cnt = (N + prm.block_ref - 1) / prm.block_ref;
     cudaStream_t st = (cudaStream_t)stream;
+    // measured on B200 (48 clouds): 128 threads x 8 points = 1,170 cycles per iteration at N = 1024; spreading the points over
+    // more warps shortens the per-thread chain (the second-level reduction handles up to 32 warps in one step)
     if (N <= 128) return launch_fps<128, 1>(xyz, B, idx, prm, st);
     if (N <= 256) return launch_fps<128, 2>(xyz, B, idx, prm, st);
-    if (N <= 512) return launch_fps<128, 4>(xyz, B, idx, prm, st);
-    if (N <= 1024) return launch_fps<128, 8>(xyz, B, idx, prm, st);
+    // measured, N = 1024 -> 512 (cycles per iteration at 1965 MHz): 128 x 8: 1,170 (round 1) | 256 x 4: 660 | 512 x 2: 427 | 1024 x 1: see
+    // o3d_debug_set bit 10;  N = 512 -> 256: 256 x 2: 330 | 512 x 1: 338
+    if (N <= 512) return launch_fps<256, 2>(xyz, B, idx, prm, st);
+    if (N <= 1024) return o3d_g_fps_wide ? launch_fps<1024, 1>(xyz, B, idx, prm, st) : launch_fps<512, 2>(xyz, B, idx, prm, st);
     if (N <= 2048) return launch_fps<256, 8>(xyz, B, idx, prm, st);
     if (N <= 4096) return launch_fps<256, 16>(xyz, B, idx, prm, st);
     if (N <= 8192) return launch_fps<512, 16>(xyz, B, idx, prm, st);

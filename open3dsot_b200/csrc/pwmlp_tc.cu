@@ -349,7 +349,8 @@ struct TcFwdEpi {
     }
     __device__ __forceinline__ void prefetch(int, int, int, int) {}
     __device__ __forceinline__ const int32_t* lift_gidx() const { return nullptr; }
-    __device__ __forceinline__ void set_tile(const int32_t*) {}
+    __device__ __forceinline__ const float* lift_s() const { return nullptr; }
+    __device__ __forceinline__ void set_tile(const int32_t*, const float4*) {}
     // Fast path = a full group of 16 positions that lies inside one pooling group (S >= 16, the set-abstraction case):
     // no per-element range or group-boundary test, the max / min / first-arg scan is local to the 16 values and is merged
     // into the running (mx, ax, mn, an) of the pooling group with two compares.  Everything else takes the element-wise path.
@@ -432,7 +433,7 @@ struct TcDgradEpi {
     LiftView lv;             // lv.z / lv.s set: the previous layer's raw output is the lifted Y0 (re-evaluated, never stored)
     float sc, sh; double d1, d2;
     float yv[16];
-    float u0, u1, u2, u3; const int32_t* gs;   // lifted: this thread's u[j][ch]; the tile's gidx slice staged in shared memory
+    float u0, u1, u2, u3; const int32_t* gs; const float4* ss;   // lifted: this thread's u[j][ch]; the tile's gidx / s slices staged in shared memory
     __device__ __forceinline__ bool lifted() const { return LIFT; }
     __device__ __forceinline__ void begin(int ch, int Nw) {
         d1 = d2 = 0.0;
@@ -445,14 +446,14 @@ struct TcDgradEpi {
         }
     }
     __device__ __forceinline__ const int32_t* lift_gidx() const { return LIFT ? lv.gidx : nullptr; }
-    __device__ __forceinline__ void set_tile(const int32_t* g) { if constexpr (LIFT) gs = g; }
+    __device__ __forceinline__ const float* lift_s() const { return LIFT ? lv.s : nullptr; }
+    __device__ __forceinline__ void set_tile(const int32_t* g, const float4* s4) { if constexpr (LIFT) { gs = g; ss = s4; } }
     // lifted yprev: `col` = first column of the group inside the tile (index into the staged gidx slice)
     __device__ __forceinline__ void prefetch_lift(int ch, int pbase, int col, int P) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const int pj = min(pbase + j, P - 1);
             const float z = lv.z ? __ldg(lv.z + (size_t)gs[col + j] * lv.ldz + ch) : 0.f;
-            const float4 sv = lv.s ? ld4g(lv.s + (size_t)pj * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 sv = lv.s ? ss[col + j] : make_float4(0.f, 0.f, 0.f, 0.f);
             yv[j] = lift_val(z, sv, u0, u1, u2, u3);
         }
     }
@@ -530,7 +531,7 @@ struct TcDgradEpi {
 template <int MT> struct TcCfg {
     static constexpr int STAGES = MT == 2 ? 2 : 3;
     static constexpr int STAGE_BYTES_ = (2 * MT + 2) * TILE_BYTES;      // MT x (Whi|Wlo) | Xhi | Xlo
-    static constexpr int SMEM = STAGES * STAGE_BYTES_ + 1024 + 256 + 1024;   // + alignment | barriers | gidx slices (lifted dgrad)
+    static constexpr int SMEM = STAGES * STAGE_BYTES_ + 1024 + 256 + 1024 + 4096;   // + alignment | barriers | gidx + s slices (lifted dgrad)
     static constexpr uint32_t TMEM = MT == 2 ? 512 : 256;
 };
 constexpr int TC2_THREADS = 576;   // 18 warps: 0 MMA | 1 weights | 2,3,12-17 producers | 4-11 epilogue
@@ -643,15 +644,22 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         epi.begin(ch, Nw);
         const int Nw_e = (dbg & 4) ? 0 : Nw;          // dbg: ch >= Nw_e -> the epilogue body is skipped
         int acc = 0, aphase = 0;
-        int32_t* gsm = reinterpret_cast<int32_t*>(smem + C::STAGES * C::STAGE_BYTES_ + 256);   // [2][TC_N]
+        int32_t* gsm = reinterpret_cast<int32_t*>(smem + C::STAGES * C::STAGE_BYTES_ + 256);   // [2][TC_N] row indices
+        float4* ssm = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES_ + 256 + 1024);   // [2][TC_N] per-position scalars
         for (int t = blockIdx.x; t < n_ptiles; t += gridDim.x) {
             const int pt0 = tile_of(t) * TC_N;
-            if (const int32_t* gi = epi.lift_gidx()) {
-                // lifted previous layer: stage the tile's 128 row indices once (warps 4-7), all 8 epilogue warps read them;
-                // the named barrier of tile t+1 orders the re-use of the slice by tile t+2
-                if (grp == 0) gsm[acc * TC_N + q * 32 + lane] = __ldg(gi + min(pt0 + q * 32 + lane, P - 1));
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                epi.set_tile(gsm + acc * TC_N);
+            {
+                // lifted previous layer: stage the tile's 128 row indices (warps 4-7) and per-position scalars (warps 8-11) once,
+                // all 8 epilogue warps read them; the named barrier of tile t+1 orders the re-use of the slices by tile t+2
+                const int32_t* gi = epi.lift_gidx();
+                const float* si = epi.lift_s();
+                if (gi || si) {
+                    const int pp = min(pt0 + q * 32 + lane, P - 1);
+                    if (gi && grp == 0) gsm[acc * TC_N + q * 32 + lane] = __ldg(gi + pp);
+                    if (si && grp == 1) ssm[acc * TC_N + q * 32 + lane] = ld4g(si + (size_t)pp * 4);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    epi.set_tile(gsm + acc * TC_N, ssm + acc * TC_N);
+                }
             }
             epi.prefetch(ch, Nw_e, pt0 + cg0 * 16, P);
             o3d_mbar_wait(tfull + acc, aphase);
@@ -1177,6 +1185,9 @@ __global__ void w_pretile_kernel(const float* __restrict__ W, int ld, int rows, 
 }
 
 int g_tc_debug = 0, g_tc_force_mt = 0;
+}  // namespace
+extern int o3d_g_fps_wide;
+namespace {
 inline int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 thread_local int g_tc_rev = 0;   // direction of the next launch (set by the stack sequencer)
 
@@ -1245,6 +1256,7 @@ extern "C" void o3d_debug_set(int tc_debug, int force_mt) {
     g_tc_debug = tc_debug;
     g_tc_force_mt = force_mt;
     o3d_g_no_skinny = (tc_debug & 128) != 0;
+    o3d_g_fps_wide = (tc_debug & 1024) != 0;
 }
 extern "C" void o3d_pw_tc_set_reverse(int rev) { g_tc_rev = rev; }
 

@@ -129,7 +129,7 @@ struct Plan {
     // forward (persisted) offsets
     size_t wp[O3D_MAX_LAYERS], wt[O3D_MAX_LAYERS], bias[O3D_MAX_LAYERS], y[O3D_MAX_LAYERS], vec[O3D_MAX_LAYERS],
         stat[O3D_MAX_LAYERS], tiles[O3D_MAX_LAYERS];
-    size_t ymax, ymin, arg, sel, ysel, stat_all, stat_bytes, fwd_bytes;
+    size_t ymax, ymin, arg, sel, ysel, stat_all, stat_bytes, fwd_bytes, param_bytes;
     // backward (temporary) offsets
     size_t bstat, bstat_bytes, coef[O3D_MAX_LAYERS], dwp[O3D_MAX_LAYERS], btiles[O3D_MAX_LAYERS], dpool, gbuf[2], wpart, bwd_bytes;
     long long wpart_floats;
@@ -166,6 +166,9 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
         p.bias[l] = o; o += al(sizeof(float) * p.Nw[l]);
         p.tiles[l] = o; if (p.tc_f[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(p.Nw[l], p.K[l]));
         p.btiles[l] = o; if (p.tc_b[l]) o += al((size_t)o3d_pw_tc_wtile_bytes(tc_main(p.K[l]), p.Nw[l]));
+    }
+    p.param_bytes = o;       // everything above depends on the parameters only (eval mode): o3d_stack_prepare() fills it once
+    for (int l = 0; l < p.n; ++l) {
         p.y[l] = o; if (!(l == 0 && p.virt)) o += al(sizeof(float) * (size_t)p.P * p.Nw[l]);
     }
     p.gidx = o; if (p.lift && d->lift->z) o += al(sizeof(int32_t) * (size_t)p.P);
@@ -206,25 +209,8 @@ inline double* stat_sum(const Plan& p, uint8_t* ws, int l) { return reinterpret_
 template <class T> inline T* at(uint8_t* ws, size_t off) { return reinterpret_cast<T*>(ws + off); }
 template <class T> inline const T* at(const uint8_t* ws, size_t off) { return reinterpret_cast<const T*>(ws + off); }
 
-}  // namespace
-
-extern "C" long long o3d_stack_workspace_bytes(const o3d_stack_t* d, int backward) {
-    Plan p;
-    if (!d || !make_plan(d, p)) return -1;
-    return (long long)(backward ? p.bwd_bytes : p.fwd_bytes);
-}
-
-extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float* out, int keep_for_backward,
-                                 void* stream) {
-    O3D_REQUIRE(d && (x || d->lift) && ws_fwd && out, O3D_ERR_ARG, "o3d_stack_forward: null pointer");
-    Plan p;
-    O3D_REQUIRE(make_plan(d, p), O3D_ERR_ARG, "o3d_stack_forward: bad stack description");
-    O3D_REQUIRE(p.S == 0 || (128 % p.S == 0 && p.P % p.S == 0), O3D_ERR_ARG, "o3d_stack_forward: group size %d", p.S);
-    if (p.P == 0) return O3D_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    uint8_t* ws = (uint8_t*)ws_fwd;
-    O3D_CUDA(cudaMemsetAsync(ws + p.stat_all, 0, p.stat_bytes, st), "o3d_stack_forward: memset");   // statistics + BN vectors
-    {   // every layer's padded weights, transposes, bias and pre-tiled images: one launch
+// every layer's padded weights, transposes, bias and pre-tiled images: one launch
+int pack_params(const o3d_stack_t* d, const Plan& p, uint8_t* ws, int keep_for_backward, cudaStream_t st) {
         PackArgs pa{};
         pa.c0 = d->c0;
         int work_max = 0;
@@ -250,6 +236,64 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
         }
         pack_weight_kernel<<<dim3((work_max + 255) / 256, p.n), 256, 0, st>>>(pa);
         O3D_CHECK_LAUNCH("o3d_stack_forward: pack_weight");
+    return O3D_OK;
+}
+
+}  // namespace
+
+extern "C" long long o3d_stack_workspace_bytes(const o3d_stack_t* d, int backward) {
+    Plan p;
+    if (!d || !make_plan(d, p)) return -1;
+    return (long long)(backward ? p.bwd_bytes : p.fwd_bytes);
+}
+
+extern "C" long long o3d_stack_prepared_bytes(const o3d_stack_t* d) {
+    Plan p;
+    if (!d || !make_plan(d, p)) return -1;
+    return (long long)p.param_bytes;
+}
+
+// Inference with static weights: pack the weights and fold the running BatchNorm statistics ONCE into `block`
+// (o3d_stack_prepared_bytes() bytes); a descriptor whose `prepared` points at it skips both in every forward call.
+// The block depends on the layer shapes AND on P's size class (which layers take the tensor-core path): prepare per shape.
+extern "C" int o3d_stack_prepare(const o3d_stack_t* d, void* block, void* stream) {
+    O3D_REQUIRE(d && block, O3D_ERR_ARG, "o3d_stack_prepare: null pointer");
+    O3D_REQUIRE(!d->training, O3D_ERR_ARG, "o3d_stack_prepare: eval mode only (train-mode BatchNorm needs the batch)");
+    Plan p;
+    O3D_REQUIRE(make_plan(d, p), O3D_ERR_ARG, "o3d_stack_prepare: bad stack description");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)block;
+    O3D_CUDA(cudaMemsetAsync(ws + p.stat_all, 0, p.stat_bytes, st), "o3d_stack_prepare: memset");
+    if (int rc = pack_params(d, p, ws, 0, st)) return rc;
+    for (int l = 0; l < p.n; ++l) {
+        if (!d->has_bn[l]) continue;
+        const int Nw = p.Nw[l];
+        float* vec = at<float>(ws, p.vec[l]);
+        if (int rc = o3d_bn_fwd_finalize(nullptr, nullptr, (double)p.P, d->gamma[l], d->beta[l], d->running_mean[l], d->running_var[l],
+                                         nullptr, d->momentum[l], d->eps[l], 0, d->cout[l], vec, vec + Nw, vec + 2 * Nw, vec + 3 * Nw,
+                                         stream))
+            return rc;
+    }
+    return O3D_OK;
+}
+
+extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float* out, int keep_for_backward,
+                                 void* stream) {
+    O3D_REQUIRE(d && (x || d->lift) && ws_fwd && out, O3D_ERR_ARG, "o3d_stack_forward: null pointer");
+    Plan p;
+    O3D_REQUIRE(make_plan(d, p), O3D_ERR_ARG, "o3d_stack_forward: bad stack description");
+    O3D_REQUIRE(p.S == 0 || (128 % p.S == 0 && p.P % p.S == 0), O3D_ERR_ARG, "o3d_stack_forward: group size %d", p.S);
+    if (p.P == 0) return O3D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)ws_fwd;
+    // Parameter block (padded / transposed / pre-tiled weights, BN scale / shift): per call in the workspace, or — inference
+    // with static weights — the block o3d_stack_prepare() filled once (no packing, no BN finalisation per call).
+    const bool prepared = d->prepared != nullptr;
+    O3D_REQUIRE(!prepared || (!d->training && !keep_for_backward), O3D_ERR_ARG, "o3d_stack_forward: a prepared block is for inference only");
+    uint8_t* wsp = prepared ? (uint8_t*)d->prepared : ws;
+    if (!prepared) {
+        O3D_CUDA(cudaMemsetAsync(ws + p.stat_all, 0, p.stat_bytes, st), "o3d_stack_forward: memset");   // statistics + BN vectors
+        if (int rc = pack_params(d, p, wsp, keep_for_backward, st)) return rc;
     }
     const float* cur = x;
     int cur_ld = d->K0;
@@ -258,13 +302,13 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
     const int L = p.n - 1;
     for (int l = 0; l < p.n; ++l) {
         const int Nw = p.Nw[l], K = p.K[l], cout = d->cout[l];
-        float* wt = at<float>(ws, p.wt[l]);
-        float* bias = d->bias[l] ? at<float>(ws, p.bias[l]) : nullptr;
+        float* wt = at<float>(wsp, p.wt[l]);
+        float* bias = d->bias[l] ? at<float>(wsp, p.bias[l]) : nullptr;
         const bool last = l == L, pool = last && p.S > 0;
         const bool keep_y = !last || keep_for_backward || !pool;
         float* y = keep_y ? at<float>(ws, p.y[l]) : nullptr;
         const bool stats = d->training && d->has_bn[l];
-        double* sum = stats ? stat_sum(p, ws, l) : nullptr;
+        double* sum = stats ? stat_sum(p, wsp, l) : nullptr;
         double* sumsq = stats ? sum + Nw : nullptr;
         float* ymax = pool ? at<float>(ws, p.ymax) : nullptr;
         float* ymin = pool ? at<float>(ws, p.ymin) : nullptr;
@@ -275,12 +319,12 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
             rc = o3d_lift_stats(d->lift, p.P, Nw, at<int32_t>(ws, p.gidx), p.virt ? nullptr : y, sum, sumsq, stream);
         } else if (l == 1 && p.virt) {
             o3d_pw_tc_set_reverse(0);
-            rc = o3d_pw_fwd_tc_lift(d->lift, at<int32_t>(ws, p.gidx), in_scale, in_shift, in_relu, ws + p.tiles[l], bias, p.P, K,
+            rc = o3d_pw_fwd_tc_lift(d->lift, at<int32_t>(ws, p.gidx), in_scale, in_shift, in_relu, wsp + p.tiles[l], bias, p.P, K,
                                     cout, y, Nw, sum, sumsq, pool ? p.S : 0, ymax, ymin, arg, Nw, stream);
         } else if (p.tc_f[l]) {
             // snake order: layer 0 starts where the grouping kernel finished (the end), layer 1 where layer 0 finished, ...
             o3d_pw_tc_set_reverse((l & 1) == 0);
-            void* tiles = ws + p.tiles[l];
+            void* tiles = wsp + p.tiles[l];
             rc = o3d_pw_fwd_tc(cur, cur_ld, in_scale, in_shift, in_relu, tiles, bias, p.P, K, cout, y, Nw, sum, sumsq,
                                pool ? p.S : 0, ymax, ymin, arg, Nw, stream);
         } else {
@@ -288,10 +332,11 @@ extern "C" int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_
                             pool ? p.S : 0, ymax, ymin, arg, Nw, stream);
         }
         if (rc) return rc;
-        float* vec = at<float>(ws, p.vec[l]);
+        float* vec = at<float>(wsp, p.vec[l]);
         float *sc = nullptr, *sh = nullptr;
         if (d->has_bn[l]) {
             sc = vec; sh = vec + Nw;
+            if (!prepared)      // prepared: scale / shift of the running statistics are already in the block
             rc = o3d_bn_fwd_finalize(sum, sumsq, (double)p.P, d->gamma[l], d->beta[l], d->running_mean[l], d->running_var[l],
                                      d->training ? d->num_batches_tracked[l] : nullptr, d->momentum[l], d->eps[l],
                                      d->training, cout, sc, sh, vec + 2 * Nw, vec + 3 * Nw, stream);

@@ -87,6 +87,7 @@ class _Meta:
         self.xyz_first = bool(xyz_first)
         self.c0 = int(c0)
         self.dx_cols = int(dx_cols)
+        self.grad_mode = torch.is_grad_enabled()   # of the CALLER (inside Function.forward grad mode is always off)
         self.bns = [s.bn for s in specs]
         self.relu = [bool(s.relu) for s in specs]
         # a spec without weight is the lifted first layer (BatchNorm / ReLU only; `lift_c0` output channels)
@@ -113,6 +114,49 @@ def _describe(meta, P, K0, params):
     return d
 
 
+def clear_prepared():
+    """kept for API symmetry: prepared blocks live ON the parameters they were built from and die with them"""
+
+
+def _versions(params):
+    return tuple(-1 if t is None else t._version for t in params)
+
+
+def _derived(weight, tag, make):
+    """A tensor computed from `weight` (e.g. a contiguous column slice).  With static weights and no autograd it is built once
+    and stored ON the weight (keyed by the weight's version counter: `load_state_dict` / in-place edits invalidate it), which
+    also keeps its address stable for the prepared-block cache."""
+    if not runtime.static_weights() or torch.is_grad_enabled():
+        return make()
+    cache = weight.__dict__.setdefault("_o3d_derived", {})
+    hit = cache.get(tag)
+    if hit is None or hit[0] != weight._version:
+        hit = cache[tag] = (weight._version, make().detach())
+    return hit[1]
+
+
+def _attach_prepared(d, meta, params, P, K0, lifted, need_grad, device):
+    """Inference with static weights: point the descriptor at the stack's prepared block (built on first use).  The block is
+    stored on the stack's first parameter tensor, keyed by the shape class and by every parameter's identity + version."""
+    if need_grad or meta.training or not runtime.static_weights():
+        return None
+    owner = next(t for t in params if t is not None)
+    cache = owner.__dict__.setdefault("_o3d_prepared", {})
+    key = (tuple(id(t) for t in params), P, K0, meta.S, lifted, runtime.tc_level(), meta.xyz_first, meta.c0)
+    ver = _versions(params)
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:
+        L = _lib.lib()
+        nbytes = L.o3d_stack_prepared_bytes(ctypes.byref(d))
+        if nbytes < 0:
+            raise RuntimeError("fused MLP stack: invalid stack description")
+        block = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        _lib.check(L.o3d_stack_prepare(ctypes.byref(d), block.data_ptr(), _stream()), "o3d_stack_prepare")
+        hit = cache[key] = (ver, block, params)          # params kept alive with the block: their ids stay unique
+    d.prepared = hit[1].data_ptr()
+    return hit[1]
+
+
 class _MLPStackFn(torch.autograd.Function):
     """x (P, K0) channels-last fp32; per layer: weight (checkpoint layout), bias|None, gamma|None, beta|None."""
 
@@ -124,7 +168,8 @@ class _MLPStackFn(torch.autograd.Function):
                 raise RuntimeError("fused MLP stack: parameters must be contiguous")
         d = _describe(meta, P, K0, params)
         L = _lib.lib()
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = meta.grad_mode and any(ctx.needs_input_grad)   # (needs_input_grad mirrors requires_grad even under no_grad)
+        _attach_prepared(d, meta, params, P, K0, False, need_grad, x.device)
         nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 0)
         if nbytes < 0:
             raise RuntimeError("fused MLP stack: invalid stack description")
@@ -200,7 +245,8 @@ class _LiftedStackFn(torch.autograd.Function):
         lf.s, lf.u = _ptr(s), _ptr(u)
         d.lift = ctypes.pointer(lf)
         L = _lib.lib()
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = meta.grad_mode and any(ctx.needs_input_grad)   # (needs_input_grad mirrors requires_grad even under no_grad)
+        _attach_prepared(d, meta, params, P, C0, (z is not None, s is not None), need_grad, dev)
         nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 0)
         if nbytes < 0:
             raise RuntimeError("lifted MLP stack: invalid stack description")
@@ -359,11 +405,11 @@ def sa_forward(sa, xyz, features, sample_idxs):
                 if grouper.normalize_xyz:
                     rel = rel / grouper.radius
                 rel = F.pad(rel, (0, 1)).contiguous()
-            u = F.pad(W2[:, :3].t(), (0, 0, 0, 1)).contiguous()                          # (4, C0): rows = W0's xyz columns, 0
+            u = _derived(W0, "u_xyz", lambda: F.pad(W2[:, :3].t(), (0, 0, 0, 1)).contiguous())   # (4, C0): rows = W0's xyz columns, 0
             z = None
             if feat_cl is not None:
-                z = mlp_stack(feat_cl.view(B * N, Cp), [_LayerSpec(W2[:, 3:].contiguous(), specs[0].bias, None, False)], 0,
-                              sa.training)
+                Wf = _derived(W0, "w_feat", lambda: W2[:, 3:].contiguous())
+                z = mlp_stack(feat_cl.view(B * N, Cp), [_LayerSpec(Wf, specs[0].bias, None, False)], 0, sa.training)
             geom = _LiftGeom(B * npoint * S, 0, N, npoint * S, S)
             pooled = lifted_stack(specs, geom, C0, z=z, ridx=idx.view(-1) if z is not None else None,
                                   s=rel.view(B * npoint * S, 4), u=u, S=S, training=sa.training)
@@ -499,11 +545,12 @@ def p2b_xcorr_forward(xc, template_feature, search_feature, template_xyz):
         C = rows.shape[2]
         if C % 4:
             rows = F.pad(rows, (0, _r4(C) - C))
-        z = mlp_stack(rows.reshape(B * n1, rows.shape[2]), [_LayerSpec(W0[:, 1:].contiguous(), specs[0].bias, None, False)], 0,
-                      xc.training)
+        Wr = _derived(specs[0].weight, "w_rest", lambda: W0[:, 1:].contiguous())
+        z = mlp_stack(rows.reshape(B * n1, rows.shape[2]), [_LayerSpec(Wr, specs[0].bias, None, False)], 0, xc.training)
         geom = _LiftGeom(B * n2 * n1, n1, n1, n2 * n1, n1)
         pooled = lifted_stack(specs, geom, z.shape[1], z=z, s=F.pad(sim_t.reshape(-1, 1), (0, 3)),
-                              u=F.pad(W0[:, :1].t(), (0, 0, 0, 3)).contiguous(), S=n1, training=xc.training)
+                              u=_derived(specs[0].weight, "u_sim", lambda: F.pad(W0[:, :1].t(), (0, 0, 0, 3)).contiguous()), S=n1,
+                              training=xc.training)
     else:
         fusion = torch.cat([sim.transpose(1, 2).unsqueeze(-1),                                      # (B,n2,n1,1)
                             template_xyz.unsqueeze(1).expand(B, n2, n1, 3),

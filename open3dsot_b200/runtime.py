@@ -30,6 +30,34 @@ def set_lift(flag: bool) -> None:
     _LIFT = bool(flag)
 
 
+# Inference with static weights (the tracking loop): eval-mode stacks pack their weights and fold their running BatchNorm
+# statistics ONCE (o3d_stack_prepare) instead of per call.  Off by default — a cached block goes stale when the weights change
+# (the engine's fused Adam updates parameters in place without bumping tensor versions): turn it on only around inference,
+# and call fused.clear_prepared() after loading new weights.
+_STATIC_WEIGHTS = False
+
+
+def static_weights() -> bool:
+    return _STATIC_WEIGHTS
+
+
+def set_static_weights(flag: bool) -> None:
+    global _STATIC_WEIGHTS
+    _STATIC_WEIGHTS = bool(flag)
+
+
+@contextlib.contextmanager
+def static_weights_scope():
+    """`with runtime.static_weights_scope():` — inference code whose weights do not change while it runs."""
+    global _STATIC_WEIGHTS
+    old = _STATIC_WEIGHTS
+    _STATIC_WEIGHTS = True
+    try:
+        yield
+    finally:
+        _STATIC_WEIGHTS = old
+
+
 def tc_enabled() -> bool:
     return _TC != 0
 

@@ -124,7 +124,9 @@ class DeviceTracker:
 
     def _frame(self):
         cfg = self.cfg
-        with torch.no_grad():
+        from .. import runtime
+        # the tracker never changes the weights: eval-mode stacks pack them / fold their BatchNorm once, not per frame
+        with torch.no_grad(), runtime.static_weights_scope():
             out = self.model(self._inputs())
             est = out["estimation_boxes"][0]                                   # (num_proposal, 5) or (4,)
             if est.dim() == 2:
