@@ -185,6 +185,9 @@ def run_track(args):
     torch.cuda.set_device(dev)
     cfg = load_config(CFG_FILE if args.cfg is None else os.path.join(ROOT, "cfgs", args.cfg), {"up_axis": [0, 0, 1]})
     torch.manual_seed(0)
+    if os.environ.get("O3D_FORCE_MT"):
+        from open3dsot_b200 import _lib
+        _lib.lib().o3d_debug_set(0, int(os.environ["O3D_FORCE_MT"]))
     net = get_model(cfg.net_model)(cfg).to(dev).eval()
     frames, npts = max(args.steps + args.warmup + 1, 12), args.track_points
     seq = synthetic_sequence(n_frames=frames, n_points=npts, seed=20260924)

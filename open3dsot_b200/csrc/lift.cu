@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(LIFT_THREADS)
     const int n_groups = P / grp;
     const U4 u = load_u(lv, c);
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!STORE && !sum) {      // inference on the tensor-core path: only the row indices are needed
+        if (lv.z && t == 0)
+            for (int g = blockIdx.x * rl + lane; g < n_groups; g += gridDim.x * rl)
+                for (int s = 0; s < grp; ++s) gidx[g * grp + s] = lift_row(geo, g * grp + s);
+        return;
+    }
     double d1[4] = {0.0, 0.0, 0.0, 0.0}, d2[4] = {0.0, 0.0, 0.0, 0.0};
     for (int g = blockIdx.x * rl + lane; g < n_groups; g += gridDim.x * rl) {
         float4 a1 = zero, a2 = zero;
@@ -213,7 +219,7 @@ extern "C" int o3d_lift_stats(const o3d_lift_t* lf, int P, int C0, int32_t* gidx
                               void* stream) {
     if (int e = lift_check(lf, P, C0, "o3d_lift_stats")) return e;
     O3D_REQUIRE(gidx || !lf->z, O3D_ERR_ARG, "o3d_lift_stats: gidx workspace missing");
-    if (P == 0) return O3D_OK;
+    if (P == 0 || (!lf->z && !y0 && !sum)) return O3D_OK;      // nothing to gather, store or count
     int threads, blocks, rl;
     lift_launch_shape(P, C0, lf->grp, threads, blocks, rl);
     const LiftView lv = make_view(lf, gidx);

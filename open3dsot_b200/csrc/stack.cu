@@ -146,14 +146,19 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
     for (int l = 0; l < p.n; ++l) {
         p.Nw[l] = r4(d->cout[l]);
         p.K[l] = l == 0 ? (p.lift ? 0 : d->K0) : p.Nw[l - 1];
-        p.tc_f[l] = (d->use_tc & 1) && (p.Nw[l] % 128 == 0 || p.Nw[l] == 64) && p.K[l] >= 32 && d->P >= 128 &&
+        // forward: also single, partly filled position tiles (P >= 16: the B = 1 tracking frame's 64 / 128-position head layers —
+        // on the CUDA-core kernel such a layer is a 256-deep serial loop on two CTAs, 38 us; here one tile, 15 us)
+        // (inference: also narrow output layers — 1 / 5 / 9 channels of the heads — as one partly filled channel tile)
+        p.tc_f[l] = (d->use_tc & 1) && (p.Nw[l] % 128 == 0 || p.Nw[l] == 64 || (!d->training && p.Nw[l] < 128)) && p.K[l] >= 32 &&
+                    d->P >= (d->training ? 128 : 16) &&
                     !(l == d->n_layers - 1 && d->S > 0 && 64 % d->S != 0);
         p.tc_b[l] = (d->use_tc & 1) && p.K[l] >= 64 && p.Nw[l] >= 32 && d->P >= 128;
     }
     if (p.lift) {
         // Y0 stays virtual when all three GEMMs of layer 1 run on the tensor cores over whole 32-channel k-blocks
         const bool tcw1 = (d->use_tc & 2) && p.Nw[1] >= 64 && p.K[1] >= 64 && d->P >= 4096;
-        p.virt = p.tc_f[1] && p.tc_b[1] && tcw1 && tc_main(p.K[1]) == p.K[1] && p.K[1] % 32 == 0 && !(d->use_tc & 8);
+        // (inference: no weight-gradient kernel will run, so its size floor P >= 4096 does not apply)
+        p.virt = p.tc_f[1] && p.tc_b[1] && (tcw1 || !d->training) && tc_main(p.K[1]) == p.K[1] && p.K[1] % 32 == 0 && !(d->use_tc & 8);
     }
     // statistics block first (one memset)
     p.stat_all = o;
