@@ -43,26 +43,52 @@ def _bat(seed=0):
     return cfg, get_model(cfg.net_model)(cfg).cuda().train()
 
 
-def test_graph_replay_matches_eager_steps():
-    cfg, net_a = _bat()
-    _, net_b = _bat()
-    net_b.load_state_dict(net_a.state_dict())
-    batches = [synthetic_siamese_batch(4, 256, 512, seed=100 + i, device="cuda") for i in range(5)]
-    eager = TrainStep(net_a, lr=cfg.lr, use_graph=False)
-    graph = TrainStep(net_b, lr=cfg.lr, use_graph=True, warmup=1)
-    la, lb = [], []
-    for b in batches:
-        la.append(float(eager.step(b)))
-        lb.append(float(graph.step(b)))
-    assert graph.graph is not None                           # the last steps really were replays
-    # step 1 is eager in both engines: identical loss.  Step 2 is the first replay: same batch, state equal up to the
-    # summation order of the fp32 REDs in step 1's weight gradients — which is already enough to flip a discrete choice
-    # (proposal top-k, ball query on predicted centres) in a 4-pair batch.  From there on the two runs are two samples of
-    # the same round-off-chaotic trajectory: only closeness of the first replayed steps is a meaningful check.
-    assert abs(la[0] - lb[0]) <= 1e-6 * abs(la[0]), (la, lb)
-    assert abs(la[1] - lb[1]) <= 2e-2 * abs(la[1]), (la, lb)
-    assert abs(la[2] - lb[2]) <= 6e-2 * abs(la[2]), (la, lb)
-    assert all(0.3 * x < y < 3.0 * x for x, y in zip(la, lb)), (la, lb)
+def _snapshot(eng):
+    return (eng.flat.flat.clone(), eng.opt.exp_avg.clone(), eng.opt.exp_avg_sq.clone(), eng.opt.state.clone(),
+            [b.clone() for b in eng.model.buffers()])
+
+
+def _restore(eng, snap):
+    with torch.no_grad():
+        eng.flat.flat.copy_(snap[0]); eng.opt.exp_avg.copy_(snap[1]); eng.opt.exp_avg_sq.copy_(snap[2]); eng.opt.state.copy_(snap[3])
+        for b, old in zip(eng.model.buffers(), snap[4]):
+            b.copy_(old)
+
+
+def test_graph_replay_equals_eager_step_from_the_same_state():
+    """Five optimisation steps at B = 4; at EVERY step the captured graph and the eager path are run from the same state
+    (parameters, Adam moments, BatchNorm buffers restored in between), so the comparison is one step deep and no trajectory
+    chaos enters: loss, the full gradient, and the Adam-updated parameters / moments must agree.  The two executions differ only
+    by the summation order of the fp32 / fp64 atomics (BatchNorm sums, the 128x128 weight-gradient tile, the scatter of the lifted
+    layer), measured at <= 2e-6 of the gradient norm; a wrong Adam step, a stale graph input or a missed BN update would show as
+    an O(1) difference."""
+    cfg, net = _bat()
+    batches = [synthetic_siamese_batch(4, 256, 512, seed=100 + i, device="cuda") for i in range(6)]
+    eng = TrainStep(net, lr=cfg.lr, use_graph=True, warmup=1)
+    eng.step(batches[0])                                      # eager warm-up step
+    worst = 0.0
+    for b in batches[1:]:
+        snap = _snapshot(eng)
+        lg = eng.step(b).clone()                              # step 2 captures the graph, later steps replay it
+        assert eng.graph is not None
+        gg, pg, mg = eng.flat.grad.clone(), eng.flat.flat.clone(), eng.opt.exp_avg.clone()
+        step_g = float(eng.opt.state[0])
+        bn_g = [x.clone() for x in net.buffers()]
+        _restore(eng, snap)
+        le = eng._eager(b).clone()
+        ge, pe, me = eng.flat.grad, eng.flat.flat, eng.opt.exp_avg
+        assert float(eng.opt.state[0]) == step_g             # both advanced the step counter once
+        assert abs(float(lg) - float(le)) <= 1e-6 * abs(float(le)), (float(lg), float(le))
+        rg = float((gg - ge).norm() / ge.norm())
+        worst = max(worst, rg)
+        assert rg < 1e-4, rg
+        assert float((mg - me).norm() / me.norm()) < 1e-4
+        # Adam's update is lr * m / (sqrt(v) + eps): bounded by lr per element, and equal wherever the gradients are
+        assert float((pg - pe).abs().max()) <= 2.0 * cfg.lr
+        assert float((pg - pe).norm() / (pe - snap[0]).norm().clamp_min(1e-12)) < 2e-2
+        for x, y in zip(bn_g, net.buffers()):                  # running statistics / num_batches_tracked
+            assert torch.allclose(x.float(), y.float(), rtol=1e-5, atol=1e-7)
+    print(f"\n[graph vs eager, same state] worst gradient difference over 5 steps: {worst:.1e}")
 
 
 def test_full_size_step_fused_vs_composed():
