@@ -130,6 +130,37 @@ def main():
             out[key + ".idx_t"], out[key + ".idx_s"] = draws["idx"][0], draws["idx"][1]
             for kk, v in d.items():
                 out[key + ".out." + kk] = np.asarray(v)
+    # ---- Waymo frame construction (datasets/waymo_data.py:114-208) by the reference's own reader on converter-format pickles
+    import pickle
+    import tempfile
+    import types
+    sys.modules["datasets.generate_waymo_sot"] = types.ModuleType("datasets.generate_waymo_sot")     # tfrecord converter: not needed
+    sys.modules["datasets.generate_waymo_sot"].generate_waymo_data = None
+    from datasets import waymo_data as rw
+    rng = np.random.default_rng(7)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "lidar")); os.makedirs(os.path.join(tmp, "annos"))
+        infos = {"seg0_obj0": []}
+        for i in range(3):
+            pts = rng.uniform(-20, 20, size=(500, 3)).astype(np.float32)
+            ang = 0.3 + 0.1 * i
+            pose = np.eye(4)
+            pose[:3, :3] = _ref_shims.Quaternion(axis=[0.1, -0.05, 1.0], radians=ang).rotation_matrix
+            pose[:3, 3] = [100.0 + 2 * i, -50.0 + i, 3.0]
+            box = np.array([4.0 + i, 1.0, 0.2, 4.2, 1.9, 1.6, 1.0, 0.5, 0.4 + 0.05 * i], dtype=np.float32)
+            lp = os.path.join(tmp, "lidar", f"seq_0_frame_{i}.pkl")
+            with open(lp, "wb") as f:
+                pickle.dump({"lidars": {"points_xyz": pts}, "frame_id": i, "scene_name": "seg0"}, f)
+            with open(lp.replace("lidar", "annos"), "wb") as f:
+                pickle.dump({"veh_to_global": pose.reshape(-1)}, f)
+            infos["seg0_obj0"].append({"PC": lp, "Box": box.copy(), "Class": "VEHICLE"})
+            out[f"waymo.{i}.points_xyz"], out[f"waymo.{i}.veh_to_global"], out[f"waymo.{i}.box"] = pts, pose, box
+        with open(os.path.join(tmp, "sot_infos_vehicle_train.pkl"), "wb") as f:
+            pickle.dump(infos, f)
+        ds = rw.WaymoDataset(tmp, "train", "VEHICLE", preloading=False, preload_offset=10)
+        for i, fr in enumerate(ds.get_frames(0, range(3))):
+            out[f"waymo.{i}.out.points"] = fr["pc"].points
+            put_box(f"waymo.{i}.out.box", fr["3d_bbox"])
     np.savez_compressed(os.path.join(HERE, "ref_tracking.npz"), **out)
     print("ref_tracking.npz", os.path.getsize(os.path.join(HERE, "ref_tracking.npz")) // 1024, "KiB,", len(out), "arrays")
 
