@@ -357,34 +357,68 @@ def measured_peaks():
 
 
 def gather_roofline(dev, batch_pairs):
-    """The fused ball-query + grouping kernel (HBM write-bound) alone, SA3-search shape, output >> L2."""
-    from open3dsot_b200 import ops
+    """The irregular kernels of the lifted set-abstraction layer, SA2-search shape at the benchmark batch (48 clouds, 256 centres x 32
+    neighbours over 512 points, 128 channels), each timed alone through the C ABI with CUDA events:
+      ball_query+relative coordinates (o3d_ballquery_group, C = 0)   writes idx + (dx, dy, dz, 0) per position
+      gather pass (o3d_lift_stats)    row indices + BatchNorm statistics of Y0 = Z[idx] + s.u (Z is L2-resident)
+      scatter pass (o3d_lift_scatter) dY0 = a*g + b + c*Y0 accumulated into dZ[idx] (vector REDs), du
+    All three are HBM-side kernels: achieved = algorithmic bytes / time against the measured copy bandwidth."""
+    import ctypes
+    from open3dsot_b200 import _lib, ops
     from open3dsot_b200.datasets.synthetic import synthetic_siamese_batch
-    B = max(batch_pairs, 48) * 4           # 192 clouds -> 816 MB written per launch (> L2)
+    L = _lib.lib()
+    B, N, M, S, C0 = max(batch_pairs, 48), 512, 256, 32, 128
     b = synthetic_siamese_batch(min(B, 64), 512, 1024, seed=1)
-    xyz = b["search_points"][:, :256].contiguous().to(dev)
-    reps = (B + xyz.shape[0] - 1) // xyz.shape[0]
-    xyz = xyz.repeat(reps, 1, 1)[:B].contiguous()
-    feat = torch.randn(B, 256, 256, device=dev)
-    new_xyz = xyz[:, :128].contiguous()
-    for _ in range(3):
-        grouped, idx = ops.ballquery_group(xyz, new_xyz, feat, 0.7, 32, False)
-    torch.cuda.synchronize()
-    n = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        grouped, idx = ops.ballquery_group(xyz, new_xyz, feat, 0.7, 32, False)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    alg_bytes = grouped.numel() * 4 + idx.numel() * 4 + xyz.numel() * 4 + new_xyz.numel() * 4 + feat.numel() * 4
+    xyz = b["search_points"][:, :N].contiguous().repeat((B + 63) // 64, 1, 1)[:B].contiguous().to(dev)
+    new_xyz = xyz[:, :M].contiguous()
+    P = B * M * S
+    st = torch.cuda.current_stream().cuda_stream
+    rel, idx = ops.ballquery_group(xyz, new_xyz, None, 0.5, S, False)
+    z = torch.randn(B * N, C0, device=dev)
+    u = torch.randn(4, C0, device=dev) * 0.3
+    g = torch.randn(P, C0, device=dev) * 1e-3
+    co = [torch.rand(C0, device=dev) + 0.5, torch.randn(C0, device=dev) * 1e-4, torch.randn(C0, device=dev) * 1e-4]
+    gidx = torch.empty(P, dtype=torch.int32, device=dev)
+    stat = torch.zeros(2 * C0, dtype=torch.float64, device=dev)
+    dz, du = torch.zeros_like(z), torch.zeros_like(u)
+    lf = _lib.LiftDesc()
+    lf.z, lf.ldz, lf.ridx, lf.ridx_mod, lf.rows_per_cloud, lf.pos_per_cloud, lf.grp = z.data_ptr(), C0, idx.data_ptr(), 0, N, M * S, S
+    lf.s, lf.u, lf.d_z, lf.d_s, lf.d_u = rel.data_ptr(), u.data_ptr(), dz.data_ptr(), None, du.data_ptr()
+    runs = {
+        "ballquery_group_kernel (ball query + relative coordinates)":
+            (lambda: ops.ballquery_group(xyz, new_xyz, None, 0.5, S, False), xyz.numel() * 4 + new_xyz.numel() * 4 + P * 4 + P * 16),
+        "lift_stats_kernel (gather pass: indices + BN statistics)":
+            (lambda: _lib.check(L.o3d_lift_stats(ctypes.byref(lf), P, C0, gidx.data_ptr(), None, stat.data_ptr(), stat.data_ptr() + 8 * C0, st),
+                                "o3d_lift_stats"), P * (4 + 4 + 16) + z.numel() * 4),
+        "lift_scatter_kernel (scatter pass: dY0 -> dZ, du)":
+            (lambda: _lib.check(L.o3d_lift_scatter(ctypes.byref(lf), P, C0, gidx.data_ptr(), None, g.data_ptr(), C0, co[0].data_ptr(),
+                                                   co[1].data_ptr(), co[2].data_ptr(), st), "o3d_lift_scatter"),
+             g.numel() * 4 + P * (4 + 16) + 2 * z.numel() * 4)}
     peaks, how = measured_peaks()
-    ach = alg_bytes / (ms * 1e-3) / 1e9
-    return {"kernel": "ballquery_group_kernel (SA3-search shape, B=%d)" % B, "bound": "hbm", "achieved": ach,
-            "peak": peaks["hbm_gbs"], "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
-            "algorithmic_bytes_per_launch": alg_bytes}
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_irregular_traffic.json")) as f:
+            traffic = json.load(f)
+    except (OSError, ValueError):
+        pass
+    out = []
+    for name, (fn, nbytes) in runs.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        n = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        ach = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": name + f", SA2-search shape, B={B}: P={P}, {C0} channels", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                    "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": traffic.get(name.split(" ")[0]), "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes})
+    return out
 
 
 def ncu_traffic(P, key="fwd"):
