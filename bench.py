@@ -511,14 +511,17 @@ def roofline_backward_probe(dev, batch_pairs):
                                      tiles.data_ptr(), P, C, C, out.data_ptr(), C, yprev.data_ptr(), C, sc.data_ptr(),
                                      sh.data_ptr(), 1, stat.data_ptr(), stat.data_ptr() + 8 * C, st), "o3d_pw_dgrad_tc")
 
-    def wgrad():
-        _lib.check(L.o3d_pw_wgrad_tc(g.data_ptr(), C, y.data_ptr(), C, a.data_ptr(), b.data_ptr(), cc.data_ptr(), None, None, 0, 0,
-                                     yprev.data_ptr(), C, sc.data_ptr(), sh.data_ptr(), 1, P, C, C, dw.data_ptr(), C, st),
-                   "o3d_pw_wgrad_tc")
+    part = torch.empty(int(L.o3d_pw_wgrad_tc2_workspace_floats()), device=dev)
+
+    def wgrad():      # the split-K kernel + ordered reduction the step uses for every tensor-core weight gradient (deterministic)
+        dw.zero_()
+        _lib.check(L.o3d_pw_wgrad_tc2(g.data_ptr(), C, y.data_ptr(), C, a.data_ptr(), b.data_ptr(), cc.data_ptr(), None, None, 0, 0,
+                                      yprev.data_ptr(), C, sc.data_ptr(), sh.data_ptr(), 1, P, C, C, dw.data_ptr(), C, part.data_ptr(),
+                                      part.numel(), st), "o3d_pw_wgrad_tc2")
     peaks, how = measured_peaks()
     res = []
     for name, fn, nbytes, key in (("pw_tc_kernel<1,TcDy,TcDgradEpi<128>> (dgrad)", dgrad, 4.0 * P * C * 4, "dgrad"),
-                                  ("pw_wgrad_tc_kernel (wgrad)", wgrad, 4.0 * P * C * 3, "wgrad")):
+                                  ("pw_wgrad_tc2_kernel<1,1> + wgrad_reduce_kernel (wgrad, split-K, deterministic)", wgrad, 4.0 * P * C * 3, "wgrad")):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

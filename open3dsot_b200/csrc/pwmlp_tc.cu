@@ -952,13 +952,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 // instead of 65k float REDs per CTA.
 //   operand tile [16 positions x 128*H channels], MN-major SWIZZLE_128B_BASE32B: atom(cb, pq) at (cb + 4*H*pq) * 512
 //   descriptor (channel half h, k-step ks): start = tile + h*2048 + ks*2*SBO, LBO = 512, SBO = 4*H*512
-constexpr int WG2_K = 16;
+// positions per pipeline stage: each producer thread must keep >= 2 float4 per operand in flight, or the bytes in flight per SM
+// (512 threads x 32 B at 16 positions x 128 channels) cap the kernel near 2.3 TB/s — measured on the 128x128 variant at the SA1
+// shapes (ncu, profiles/r2_step_dram_final.txt: 278 us for 629 MB); the single-accumulator variant therefore takes 32 positions
+template <int MH, int NH> constexpr int wg2_k() { return MH * NH == 1 ? 32 : 16; }
 constexpr int WG2_STAGES = 3;
 constexpr int WG2_THREADS = 576;   // warps: 0 MMA | 1 prefetch | 2-17 producers (4-11 also run the epilogue)
 
 template <int MH, int NH> struct Wg2Cfg {
-    static constexpr int A_BYTES = WG2_K * 128 * MH * 4;            // one of hi / lo
-    static constexpr int B_BYTES = WG2_K * 128 * NH * 4;
+    static constexpr int K = wg2_k<MH, NH>();
+    static constexpr int A_BYTES = K * 128 * MH * 4;            // one of hi / lo
+    static constexpr int B_BYTES = K * 128 * NH * 4;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int SMEM = WG2_STAGES * STAGE + 1024 + 256;
     static constexpr uint32_t TMEM = (MH * NH * 128) <= 128 ? 128 : ((MH * NH * 128) <= 256 ? 256 : 512);
@@ -995,6 +999,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.z * 128 * MH, n0 = blockIdx.y * 128 * NH;
     const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
+    constexpr int WG2_K = C::K;
     const int nkb = pend > pbeg ? (pend - pbeg + WG2_K - 1) / WG2_K : 0;
     auto kpos = [&](int i) { return pbeg + i * WG2_K; };
 
@@ -1391,7 +1396,7 @@ int launch_wgrad2(const TcDy& da, const XB& xb, int P, int Cout, int Cin, float*
     if (splits > cap) splits = (int)cap;
     O3D_REQUIRE(splits >= 1, O3D_ERR_ARG, "o3d_pw_wgrad_tc2: workspace too small");
     int chunk = (P + splits - 1) / splits;
-    chunk = ((chunk + WG2_K - 1) / WG2_K) * WG2_K;
+    chunk = ((chunk + C::K - 1) / C::K) * C::K;
     splits = (P + chunk - 1) / chunk;
     kern<<<dim3(splits, nt, mt), WG2_THREADS, C::SMEM, st>>>(da, xb, P, Cout, Cin, chunk, part, g_tc_debug);
     O3D_CHECK_LAUNCH("o3d_pw_wgrad_tc2");
@@ -1440,7 +1445,7 @@ extern "C" int o3d_pw_wgrad_tc_lift(const float* g, int ldg, const float* y, int
     if (P == 0) return O3D_OK;
     TcDy da{g, ldg, y, ldy, a, b, cc, dpool, sel, S > 0 ? S : 1, ldp, ilog2_exact(S > 0 ? S : 1), g_tc_debug};
     TcLift xb = make_tclift(lf, gidx, in_scale, in_shift, in_relu);
-    xb.la = part ? WG2_K : TC_K;      // a producer thread's next fetch lies one k-block of positions further
+    xb.la = part ? ((Cout > 128 || Cin > 128) ? 16 : 32) : TC_K;      // a producer thread's next fetch lies one k-block of positions further
     if (part) return dispatch_wgrad2(da, xb, P, Cout, Cin, dw, lddw, part, part_floats, (cudaStream_t)stream);
     return launch_wgrad1(da, xb, P, Cout, Cin, dw, lddw, (cudaStream_t)stream);
 }
