@@ -175,29 +175,30 @@ def test_whole_model_against_reference_golden(gmod, mode, name, cfg_file, B, see
     net = net.cuda().train()
     batch = synthetic_siamese_batch(B, 256, 512, seed=1234 + seed, box_aware=(name == "bat"), device="cuda")
     batch["box_label"] = torch.tensor(gmod[f"{name}_box_label"], device="cuda")
-    # Whole-model tolerance is looser than the per-module 1e-4: vote clustering ball-queries COMPUTED coordinates and
-    # BoxAware takes a top-k of COMPUTED box clouds, so fp32 round-off differences between the CPU reference run and
-    # the GPU can flip a neighbour choice; every module is held to 1e-4 on identical inputs in the tests above.
+    # Measured on a B200 (round 2, fused path): BAT  cla 4.1e-5, votes / centres 1.3e-5, boxes 3.6e-5, eval boxes 3.6e-5, loss 2e-6;
+    # P2B (2 pairs of 256 / 512 points: BatchNorm over few positions amplifies round-off — the reference's own composition on torch
+    # CUDA ops deviates from its CPU run by 3e-4 here) cla 2.4e-3, votes 5.2e-4, boxes 2.1e-3, eval boxes 3.0e-5, loss 2.3e-4.
+    # The bounds below are ~4x those values; the full-size, flip-free comparison is tests/test_gpu_parity_full.py.
     with torch.no_grad():
         ep = net(batch)
     assert np.array_equal(ep["sample_idxs"].cpu().numpy(), gmod[f"{name}_sample_idxs"])
-    # seed scores, votes and proposal centres come before any data-dependent neighbour choice on computed values (P2B)
-    # or only after the box-cloud top-k (BAT): hold them tight; boxes (after the vote ball-query) loosely.
-    # P2B at B=1 normalises over a single sample's positions: CPU-vs-GPU round-off is amplified (the composed path, i.e.
-    # the reference's own composition on torch CUDA ops, deviates from the CPU run by the same ~1e-2)
-    tight = 1e-3 if name == "bat" else 3e-2
+    tight = 2e-4 if name == "bat" else 1e-2
+    print(f"\n[golden {name} {mode}] train fwd: " + ", ".join(f"{k} {rel(ep[k], gmod[f'{name}_{k}']):.1e}" for k in
+                                                            ("estimation_cla", "vote_xyz", "center_xyz", "estimation_boxes")))
     for k in ("estimation_cla", "vote_xyz", "center_xyz"):
         assert rel(ep[k], gmod[f"{name}_{k}"]) < tight, k
-    assert rel(ep["estimation_boxes"], gmod[f"{name}_estimation_boxes"]) < 5e-2
+    assert rel(ep["estimation_boxes"], gmod[f"{name}_estimation_boxes"]) < tight
     net.load_state_dict(base)
     net.eval()
     with torch.no_grad():
         ep = net(batch)
-    assert rel(ep["estimation_boxes"], gmod[f"{name}_eval_boxes"]) < 5e-2
+    print(f"[golden {name} {mode}] eval boxes {rel(ep['estimation_boxes'], gmod[f'{name}_eval_boxes']):.1e}")
+    assert rel(ep["estimation_boxes"], gmod[f"{name}_eval_boxes"]) < 2e-4
     net.load_state_dict(base)
     net.train()
     loss = net.training_step({k: v.clone() for k, v in batch.items()}, 0)
-    assert rel(loss, gmod[f"{name}_loss"]) < 2e-2
+    print(f"[golden {name} {mode}] loss {rel(loss, gmod[f'{name}_loss']):.1e}")
+    assert rel(loss, gmod[f"{name}_loss"]) < (1e-4 if name == "bat" else 1e-3)
     loss.backward()
     sd = dict(net.named_parameters())
     norms = np.array([float(sd[k].grad.norm()) for k in sorted(sd)])
