@@ -1394,6 +1394,12 @@ int launch_wgrad2(const TcDy& da, const XB& xb, int P, int Cout, int Cin, float*
     if (splits < 1) splits = 1;
     const long long cap = part_floats / ((long long)Mt * Nt);
     if (splits > cap) splits = (int)cap;
+    // small problems (the heads: a few thousand positions): every split writes and the reduction re-reads a whole Mt x Nt partial
+    // tile (256 KB for 256 x 256), so 148 splits of ~40 positions each move 77 MB for a 6,144-position layer — more than the
+    // layer itself.  At least 128 positions per split (512 was measured and is worse: the split's pipeline is a serial chain of
+    // k-blocks, 0.75 us each, and a dozen CTAs cannot hide it).
+    const int by_size = (P + 127) / 128;
+    if (splits > by_size) splits = by_size;
     O3D_REQUIRE(splits >= 1, O3D_ERR_ARG, "o3d_pw_wgrad_tc2: workspace too small");
     int chunk = (P + splits - 1) / splits;
     chunk = ((chunk + C::K - 1) / C::K) * C::K;
