@@ -169,6 +169,7 @@ int o3d_bn_fwd_finalize(const double* sum, const double* sumsq, double count, co
                         float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
                         float eps, int training, int C, float* scale, float* shift, float* mean, float* invstd,
                         void* stream);
+/* `training`: bit 0 = batch statistics were used; bit 1 = ACCUMULATE into dgamma / dbeta instead of overwriting them. */
 int o3d_bn_bwd_finalize(const double* s1, const double* s2y, double count, const float* gamma, const float* mean,
                         const float* invstd, int training, int C, float* a, float* b, float* cc, float* dgamma,
                         float* dbeta, void* stream);
@@ -265,6 +266,8 @@ typedef struct o3d_stack_t {
     float* d_gamma[O3D_MAX_LAYERS];
     float* d_beta[O3D_MAX_LAYERS];
     const o3d_lift_t* lift;   /* non-NULL: layer 0 is lifted (weight[0] == NULL, cout[0] = C0, K0 = round4(C0), x unused) */
+    int accumulate;           /* backward: d_weight / d_bias / d_gamma / d_beta are ADDED to (the caller's persistent .grad buffers —
+                                 saves one elementwise add per parameter and call); 0 = overwritten                            */
     const void* prepared;     /* non-NULL (inference only): parameter block filled by o3d_stack_prepare(); the forward then
                                  neither packs weights nor finalises BatchNorm                                            */
 } o3d_stack_t;

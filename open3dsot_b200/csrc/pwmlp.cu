@@ -745,8 +745,10 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ s1, const doub
     const double mu = mean[c], istd = invstd[c], g = gamma ? gamma[c] : 1.0;
     const double sum_g = s1[c];
     const double sum_gx = (s2y[c] - mu * sum_g) * istd;  // sum g * xhat
-    if (dgamma) dgamma[c] = (float)sum_gx;
-    if (dbeta) dbeta[c] = (float)sum_g;
+    const bool acc = (training & 2) != 0;          // bit 1: accumulate into dgamma / dbeta (caller-owned .grad buffers)
+    training &= 1;
+    if (dgamma) dgamma[c] = (acc ? dgamma[c] : 0.f) + (float)sum_gx;
+    if (dbeta) dbeta[c] = (acc ? dbeta[c] : 0.f) + (float)sum_g;
     const double aa = g * istd;
     if (training) {
         const double c2 = -aa * istd * sum_gx / count;

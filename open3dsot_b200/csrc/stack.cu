@@ -99,7 +99,7 @@ __global__ void pack_weight_kernel(const PackArgs args) {
 }
 
 struct UnpackLayer { const float* dwp; float* dst; int cout, cin, K, xyz_first; };
-struct UnpackArgs { UnpackLayer l[O3D_MAX_LAYERS]; int c0; };
+struct UnpackArgs { UnpackLayer l[O3D_MAX_LAYERS]; int c0; int accumulate; };
 
 // padded / re-ordered weight gradients -> the checkpoint layout, all layers of a stack in one launch (blockIdx.y = layer)
 __global__ void unpack_wgrad_kernel(const UnpackArgs args) {
@@ -111,12 +111,15 @@ __global__ void unpack_wgrad_kernel(const UnpackArgs args) {
     if (!dst || i >= cout * K) return;
     const int n = i / K, k = i % K;
     const int sc = src_col(k, K, cin, xyz_first, c0);
-    if (sc >= 0) dst[(size_t)n * cin + sc] = dwp[i];
+    if (sc >= 0) {
+        float* o = dst + (size_t)n * cin + sc;
+        *o = args.accumulate ? *o + dwp[i] : dwp[i];
+    }
 }
 
-__global__ void d2f_kernel(const double* __restrict__ src, int n, float* __restrict__ dst) {
+__global__ void d2f_kernel(const double* __restrict__ src, int n, float* __restrict__ dst, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (float)src[i];
+    if (i < n) dst[i] = (accumulate ? dst[i] : 0.f) + (float)src[i];
 }
 
 // ---- workspace plan -------------------------------------------------------------------------------------------
@@ -407,13 +410,15 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
         const float *a = nullptr, *b = nullptr, *cc = nullptr;
         const float* vec = at<float>(wf, p.vec[l]);
         if (d->has_bn[l]) {
-            rc = o3d_bn_bwd_finalize(s1(l), s1(l) + Nl, (double)p.P, d->gamma[l], vec + 2 * Nl, vec + 3 * Nl, d->training,
+            rc = o3d_bn_bwd_finalize(s1(l), s1(l) + Nl, (double)p.P, d->gamma[l], vec + 2 * Nl, vec + 3 * Nl,
+                                     (d->training ? 1 : 0) | (d->accumulate ? 2 : 0),
                                      cout, coef, coef + Nl, coef + 2 * Nl, d->d_gamma[l], d->d_beta[l], stream);
             if (rc) return rc;
             a = coef; b = coef + Nl; cc = coef + 2 * Nl;
-            if (d->d_bias[l]) O3D_CUDA(cudaMemsetAsync(d->d_bias[l], 0, sizeof(float) * cout, st), "d_bias");  // BN removes the mean
+            if (d->d_bias[l] && !d->accumulate)      // BN removes the mean: the bias gradient is zero (nothing to add when accumulating)
+                O3D_CUDA(cudaMemsetAsync(d->d_bias[l], 0, sizeof(float) * cout, st), "d_bias");
         } else if (d->d_bias[l]) {
-            d2f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(s1(l), cout, d->d_bias[l]);
+            d2f_kernel<<<(cout + 127) / 128, 128, 0, st>>>(s1(l), cout, d->d_bias[l], d->accumulate);
         }
         if (l == 0 && p.lift) {
             // the lifted layer has no GEMM: dY0 = a*g + b + cc*Y0 is scattered into dZ / dcc / ds / du
@@ -505,6 +510,7 @@ extern "C" int o3d_stack_backward(const o3d_stack_t* d, const float* x, const vo
     {
         UnpackArgs ua{};
         ua.c0 = d->c0;
+        ua.accumulate = d->accumulate;
         int work_max = 0;
         for (int l = 0; l < p.n; ++l) {
             UnpackLayer& q = ua.l[l];

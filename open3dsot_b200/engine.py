@@ -83,7 +83,9 @@ class TrainStep:
     def _fwd_bwd(self, batch):
         self.flat.zero_grad()
         loss = self.model.training_step(dict(batch), 0)
-        loss.backward()
+        from . import runtime
+        with runtime.grad_inplace_scope():       # parameter gradients are added straight into the flat bucket's views
+            loss.backward()
         return loss.detach()
 
     def _finish(self):

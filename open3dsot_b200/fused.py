@@ -157,6 +157,32 @@ def _attach_prepared(d, meta, params, P, K0, lifted, need_grad, device):
     return hit[1]
 
 
+def _param_grad_targets(ctx_needs, params, d, meta, first_param_index):
+    """Where a stack's backward writes its parameter gradients.  Default: fresh tensors returned to autograd.  Inside
+    `runtime.grad_inplace_scope()` and when EVERY parameter that needs a gradient is a leaf with a pre-allocated contiguous `.grad`
+    (the engine's flat bucket): the kernels add into those buffers directly and autograd gets None for them."""
+    need = [(l, j) for l in range(meta.n) for j in range(4)
+            if params[4 * l + j] is not None and ctx_needs[first_param_index + 4 * l + j]]
+    inplace = runtime.grad_inplace() and bool(need) and all(
+        params[4 * l + j].is_leaf and params[4 * l + j].grad is not None and params[4 * l + j].grad.is_contiguous()
+        and params[4 * l + j].grad.dtype == torch.float32 for l, j in need)
+    grads = [None] * (4 * meta.n)
+    fields = (d.d_weight, d.d_bias, d.d_gamma, d.d_beta)
+    for l in range(meta.n):
+        for j in range(4):
+            fields[j][l] = None
+    for l, j in need:
+        t = params[4 * l + j]
+        if inplace:
+            fields[j][l] = t.grad.data_ptr()
+        else:
+            gt = torch.empty_like(t)
+            grads[4 * l + j] = gt
+            fields[j][l] = gt.data_ptr()
+    d.accumulate = int(inplace)
+    return grads
+
+
 class _MLPStackFn(torch.autograd.Function):
     """x (P, K0) channels-last fp32; per layer: weight (checkpoint layout), bias|None, gamma|None, beta|None."""
 
@@ -195,17 +221,7 @@ class _MLPStackFn(torch.autograd.Function):
             dpad = torch.zeros(out.shape, dtype=torch.float32, device=x.device)
             dpad[:, :dout.shape[1]] = dout
             dout = dpad
-        grads = [None] * (4 * meta.n)
-        fields = (d.d_weight, d.d_bias, d.d_gamma, d.d_beta)
-        for l in range(meta.n):
-            for j in range(4):
-                t = params[4 * l + j]
-                if t is not None and ctx.needs_input_grad[2 + 4 * l + j]:
-                    gt = torch.empty_like(t)
-                    grads[4 * l + j] = gt
-                    fields[j][l] = gt.data_ptr()
-                else:
-                    fields[j][l] = None
+        grads = _param_grad_targets(ctx.needs_input_grad, params, d, meta, 2)
         dx = torch.empty(P, K0, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[1] else None
         L = _lib.lib()
         nbytes = L.o3d_stack_workspace_bytes(ctypes.byref(d), 1)
@@ -271,17 +287,7 @@ class _LiftedStackFn(torch.autograd.Function):
             dpad = torch.zeros(out.shape, dtype=torch.float32, device=out.device)
             dpad[:, :dout.shape[1]] = dout
             dout = dpad
-        grads = [None] * (4 * meta.n)
-        fields = (d.d_weight, d.d_bias, d.d_gamma, d.d_beta)
-        for l in range(meta.n):
-            for j in range(4):
-                t = params[4 * l + j]
-                if t is not None and ctx.needs_input_grad[7 + 4 * l + j]:
-                    gt = torch.empty_like(t)
-                    grads[4 * l + j] = gt
-                    fields[j][l] = gt.data_ptr()
-                else:
-                    fields[j][l] = None
+        grads = _param_grad_targets(ctx.needs_input_grad, params, d, meta, 7)
         need = ctx.needs_input_grad
         dz = torch.zeros_like(z) if (z is not None and need[3]) else None
         ds = torch.zeros_like(s) if (s is not None and need[5]) else None

@@ -58,6 +58,28 @@ def static_weights_scope():
         _STATIC_WEIGHTS = old
 
 
+# In-place accumulation of parameter gradients: a stack's backward ADDS its weight / bias / BatchNorm gradients straight into the
+# parameters' existing `.grad` buffers (and returns no gradient for them) instead of materialising them and letting autograd's
+# AccumulateGrad issue one elementwise add per parameter — ~130 launches per BAT step.  Only valid for `loss.backward()` onto
+# pre-allocated `.grad` buffers (the engine's flat bucket); `torch.autograd.grad` callers must leave it off (default).
+_GRAD_INPLACE = False
+
+
+def grad_inplace() -> bool:
+    return _GRAD_INPLACE
+
+
+@contextlib.contextmanager
+def grad_inplace_scope():
+    global _GRAD_INPLACE
+    old = _GRAD_INPLACE
+    _GRAD_INPLACE = True
+    try:
+        yield
+    finally:
+        _GRAD_INPLACE = old
+
+
 def tc_enabled() -> bool:
     return _TC != 0
 

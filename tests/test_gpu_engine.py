@@ -113,3 +113,22 @@ def test_full_size_step_fused_vs_composed():
     assert abs(lf - lc) <= 5e-3 * abs(lc), (lf, lc)
     cos = torch.dot(gf, gc) / (gf.norm() * gc.norm())
     assert float(cos) > 0.99                                # neighbour / top-k flips on computed coordinates aside
+
+
+def test_inplace_gradient_accumulation_matches_autograd_accumulation():
+    """The engine lets every stack add its parameter gradients straight into the flat bucket (runtime.grad_inplace_scope);
+    the result must equal what autograd's own accumulation produces from the same state and batch (shared backbone weights
+    receive two contributions per step either way)."""
+    cfg, net = _bat(seed=3)
+    batch = synthetic_siamese_batch(4, 256, 512, seed=7, device="cuda")
+    eng = TrainStep(net, lr=cfg.lr, use_graph=False)
+    eng._fwd_bwd(batch)                                        # in-place path
+    g_in = eng.flat.grad.clone()
+    bn = [b.clone() for b in net.buffers()]
+    eng.flat.zero_grad()
+    loss = net.training_step({k: v.clone() for k, v in batch.items()}, 0)
+    loss.backward()                                            # plain autograd accumulation into the same .grad views
+    g_ag = eng.flat.grad
+    assert float(g_ag.norm()) > 0
+    assert float((g_in - g_ag).norm() / g_ag.norm()) < 1e-5
+    assert len(bn) > 0
