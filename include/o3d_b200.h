@@ -284,6 +284,20 @@ int o3d_stack_forward(const o3d_stack_t* d, const float* x, void* ws_fwd, float*
 int o3d_stack_backward(const o3d_stack_t* d, const float* x, const void* ws_fwd, void* ws_bwd, const float* out,
                        const float* dout, float* dx, void* stream);
 
+/* A whole set-abstraction layer in ONE kernel, inference only (running BatchNorm statistics, no saved tensors): replaces the
+ * body of _PointnetSAModuleBase.forward — QueryAndGroup (pointnet2/utils/pointnet2_utils.py:299-339), the SharedMLP and the
+ * max-pool over nsample (pointnet2/utils/pointnet2_modules.py:58-76) — for one (grouper, mlp) scale.
+ * d describes the SharedMLP in the reference's layout: xyz_first = 1, c0 = feature channels C, cin[0] = 3 + C, every cout <= 256,
+ * C <= 256; P / K0 / S / training / lift are ignored.  o3d_sa_fused_prepare() packs the weights (pre-tiled TF32 hi | lo images) and
+ * folds BatchNorm + bias into per-channel scale / shift once; `block` (o3d_sa_fused_prepared_bytes() bytes) then serves every call.
+ * xyz [B, N, 3], new_xyz [B, M, 3], feat_cl [B, N, ldf] channels-last (NULL iff c0 == 0), out [B * M, ldo] channels-last,
+ * idx (nullable) [B, M, nsample] receives the ball-query result.  nsample must divide 64 and M be a multiple of 64 / nsample. */
+long long o3d_sa_fused_prepared_bytes(const o3d_stack_t* d);
+int o3d_sa_fused_prepare(const o3d_stack_t* d, void* block, void* stream);
+int o3d_sa_fused_forward(const o3d_stack_t* d, const void* block, const float* xyz, const float* new_xyz, const float* feat_cl,
+                         int ldf, int B, int N, int M, float radius, int nsample, int normalize, float* out, int ldo, int32_t* idx,
+                         void* stream);
+
 /* Lifted first layer (o3d_lift_t), helpers used by o3d_stack_forward/backward.
  * o3d_lift_stats : gidx[p] = global Z row of position p; sum / sumsq (nullable) += per-channel batch statistics of Y0;
  *                  y0 (nullable) receives Y0 itself [P, C0] (the CUDA-core fallback reads it as an ordinary activation).

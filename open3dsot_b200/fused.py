@@ -360,6 +360,65 @@ def from_channels_last(cl):
     return cl.transpose(1, 2)
 
 
+# ---------------------------------------------------------------------------------------------- single-kernel SA layer (inference)
+def _sa_fused_ok(specs, S, npoint, N, C):
+    """shape range of o3d_sa_fused_forward (csrc/sa_fused.cu): nsample | 64, <= 256 channels per layer, BatchNorm with running stats"""
+    if not runtime.sa_fused_enabled() or runtime.CHOICE_HOOK is not None or not runtime.fused_enabled():
+        return False
+    if S < 1 or 64 % S != 0 or npoint % (64 // S) != 0 or C > 256 or N * 12 > 96 * 1024 or len(specs) > _lib.MAX_LAYERS:
+        return False
+    for s in specs:
+        if s.weight is None or s.weight.shape[0] > 256:
+            return False
+        if s.bn is not None and (not s.bn.track_running_stats or s.bn.running_mean is None):
+            return False
+    return specs[0].weight.numel() // specs[0].weight.shape[0] == C + 3
+
+
+def _sa_fused_block(d, params, bns, device):
+    """the layer's parameter block (pre-tiled weight images, folded BatchNorm): built per call, or — static weights — once,
+    stored on the first weight and keyed by every parameter's / running statistic's identity and version"""
+    L = _lib.lib()
+
+    def make():
+        nbytes = L.o3d_sa_fused_prepared_bytes(ctypes.byref(d))
+        if nbytes < 0:
+            raise RuntimeError("fused SA layer: SharedMLP outside the kernel's range")
+        block = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _lib.check(L.o3d_sa_fused_prepare(ctypes.byref(d), block.data_ptr(), _stream()), "o3d_sa_fused_prepare")
+        return block
+
+    if not runtime.static_weights():
+        return make()
+    stats = [t for bn in bns if bn is not None for t in (bn.running_mean, bn.running_var)]
+    owner = params[0]
+    cache = owner.__dict__.setdefault("_o3d_sa_fused", {})
+    key = tuple(id(t) for t in params) + tuple(id(t) for t in stats)
+    ver = _versions(params) + _versions(stats)
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:
+        hit = cache[key] = (ver, make(), params, stats)
+    return hit[1]
+
+
+def _sa_fused_forward(specs, xyz, new_xyz, feat_cl, C, radius, S, normalize):
+    """one kernel: ball query + grouping + SharedMLP (running-statistics BatchNorm, ReLU) + max-pool -> (B, npoint, Cout) channels-last"""
+    B, N, _ = xyz.shape
+    npoint = new_xyz.shape[1]
+    meta = _Meta(specs, S, False, xyz_first=True, c0=C)
+    params = []
+    for s in specs:
+        params += [s.weight, s.bias, s.bn.weight if s.bn is not None else None, s.bn.bias if s.bn is not None else None]
+    d = _describe(meta, B * npoint * S, _r4(C) + 4, params)
+    block = _sa_fused_block(d, params, meta.bns, xyz.device)
+    ldo = _r4(meta.cout[-1])
+    out = torch.empty(B, npoint, ldo, dtype=torch.float32, device=xyz.device)
+    _lib.check(_lib.lib().o3d_sa_fused_forward(ctypes.byref(d), block.data_ptr(), xyz.data_ptr(), new_xyz.data_ptr(), _ptr(feat_cl),
+                                               0 if feat_cl is None else feat_cl.shape[2], B, N, npoint, float(radius), S,
+                                               int(bool(normalize)), out.data_ptr(), ldo, None, _stream()), "o3d_sa_fused_forward")
+    return out if ldo == meta.cout[-1] else out[:, :, :meta.cout[-1]]
+
+
 # ---------------------------------------------------------------------------------------------- modules
 def seq_forward(module, x):
     """Seq / SharedMLP-on-1D / bare Conv1d applied to x (B, C, L) -> (B, Cout, L) (channels-last view)."""
@@ -392,6 +451,11 @@ def sa_forward(sa, xyz, features, sample_idxs):
         if not grouper.use_xyz:
             raise RuntimeError("fused SA layer expects use_xyz=True (every shipped model does)")
         need_xyz = torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad)
+        if not sa.training and not torch.is_grad_enabled() and _sa_fused_ok(specs, S, npoint, N, C):
+            xyz_c = xyz if xyz.is_contiguous() else xyz.contiguous()
+            pooled = _sa_fused_forward(specs, xyz_c, new_xyz, feat_cl, C, grouper.radius, S, grouper.normalize_xyz)
+            outs.append(from_channels_last(pooled))
+            continue
         if _liftable(specs, "sa", {"N": N, "npoint": npoint, "S": S, "C": C}) and (specs[0].bias is None or feat_cl is not None):
             # Lifted first layer: W0 . [x(idx) - c, f(idx)] = (W0_f . f)[idx] + W0_x . (x(idx) - c) — the feature part of the
             # convolution runs once per SOURCE point (z) and is gathered; the relative coordinates (dx, dy, dz) are applied per

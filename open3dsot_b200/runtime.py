@@ -34,6 +34,19 @@ def set_lift(flag: bool) -> None:
 # statistics ONCE (o3d_stack_prepare) instead of per call.  Off by default — a cached block goes stale when the weights change
 # (the engine's fused Adam updates parameters in place without bumping tensor versions): turn it on only around inference,
 # and call fused.clear_prepared() after loading new weights.
+_SA_FUSED = os.environ.get("O3D_SA_FUSED", "1") != "0"
+
+
+def sa_fused_enabled() -> bool:
+    """eval-mode forward passes (no autograd) run every set-abstraction layer as ONE kernel (csrc/sa_fused.cu)"""
+    return _SA_FUSED
+
+
+def set_sa_fused(flag: bool) -> None:
+    global _SA_FUSED
+    _SA_FUSED = bool(flag)
+
+
 _STATIC_WEIGHTS = False
 
 
