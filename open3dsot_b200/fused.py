@@ -122,6 +122,17 @@ def _versions(params):
     return tuple(-1 if t is None else t._version for t in params)
 
 
+def _cacheable():
+    """A cached tensor may be read from another stream (the template / search branches run side by side, fused.run_ahead) with no
+    ordering against the stream that built it.  Outside graph capture the builder therefore finishes before the entry becomes
+    visible (`_publish`); during capture nothing is cached — whatever is missing is built privately, as part of the graph."""
+    return not torch.cuda.is_current_stream_capturing()
+
+
+def _publish():
+    torch.cuda.current_stream().synchronize()
+
+
 def _derived(weight, tag, make):
     """A tensor computed from `weight` (e.g. a contiguous column slice).  With static weights and no autograd it is built once
     and stored ON the weight (keyed by the weight's version counter: `load_state_dict` / in-place edits invalidate it), which
@@ -131,7 +142,10 @@ def _derived(weight, tag, make):
     cache = weight.__dict__.setdefault("_o3d_derived", {})
     hit = cache.get(tag)
     if hit is None or hit[0] != weight._version:
+        if not _cacheable():
+            return make().detach()
         hit = cache[tag] = (weight._version, make().detach())
+        _publish()
     return hit[1]
 
 
@@ -152,7 +166,10 @@ def _attach_prepared(d, meta, params, P, K0, lifted, need_grad, device):
             raise RuntimeError("fused MLP stack: invalid stack description")
         block = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
         _lib.check(L.o3d_stack_prepare(ctypes.byref(d), block.data_ptr(), _stream()), "o3d_stack_prepare")
-        hit = cache[key] = (ver, block, params)          # params kept alive with the block: their ids stay unique
+        hit = (ver, block, params)                        # params kept alive with the block: their ids stay unique
+        if _cacheable():
+            cache[key] = hit
+            _publish()
     d.prepared = hit[1].data_ptr()
     return hit[1]
 
@@ -388,7 +405,7 @@ def _sa_fused_block(d, params, bns, device):
         _lib.check(L.o3d_sa_fused_prepare(ctypes.byref(d), block.data_ptr(), _stream()), "o3d_sa_fused_prepare")
         return block
 
-    if not runtime.static_weights():
+    if not runtime.static_weights() or not _cacheable():
         return make()
     stats = [t for bn in bns if bn is not None for t in (bn.running_mean, bn.running_var)]
     owner = params[0]
@@ -398,6 +415,7 @@ def _sa_fused_block(d, params, bns, device):
     hit = cache.get(key)
     if hit is None or hit[0] != ver:
         hit = cache[key] = (ver, make(), params, stats)
+        _publish()
     return hit[1]
 
 
@@ -723,3 +741,39 @@ def fps_ahead(points, npoint):
         cur.wait_stream(side)
         return idx
     return join
+
+
+def _tensors(obj):
+    if torch.is_tensor(obj):
+        yield obj
+    elif isinstance(obj, (tuple, list)):
+        for o in obj:
+            yield from _tensors(o)
+
+
+def run_ahead(fn):
+    """Inference only (no autograd): run `fn()` — a whole branch of the network, e.g. the template backbone — on the side stream
+    and return `join()`, which makes the current stream wait for it and hands over fn's result.  At B = 1 a branch occupies a
+    handful of SMs (one CTA per cloud in FPS, 2-8 CTAs per layer), so the template and search branches — independent until the
+    cross-correlation — run side by side; inside a captured CUDA graph the fork / join becomes two parallel branches."""
+    assert not torch.is_grad_enabled(), "run_ahead is for inference (autograd does not see the stream switch)"
+    cur = torch.cuda.current_stream()
+    dev = cur.device
+    side = _SIDE_STREAMS.get(dev.index)
+    if side is None:
+        side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        result = fn()
+
+    def join():
+        cur.wait_stream(side)
+        for t in _tensors(result):
+            t.record_stream(cur)
+        return result
+    return join
+
+
+def branch_overlap(x):
+    """template / search branches on two streams: inference on the device, fused execution"""
+    return x.is_cuda and not torch.is_grad_enabled() and runtime.fused_enabled() and runtime.branch_overlap_enabled()

@@ -55,21 +55,33 @@ class BAT(base_model.MatchingBaseModel):
     def forward(self, input_dict):
         """input_dict: template_points (B,M,3), search_points (B,N,3), points2cc_dist_t (B,M,9) [+ labels]."""
         template, search = input_dict['template_points'], input_dict['search_points']
-        template_bc = input_dict['points2cc_dist_t']
+        bc_t = input_dict['points2cc_dist_t']
         M, N = template.shape[1], search.shape[1]
-        join = None
-        if self.config.use_fps and runtime.fused_enabled() and search.is_cuda:
+        fused = None
+        if runtime.fused_enabled() and search.is_cuda:
             from .. import fused
-            join = fused.fps_ahead(search, N // 2)           # search-branch FPS runs underneath the template branch
-        template_xyz, template_feature, sample_idxs_t = self.backbone(template, [M // 2, M // 4, M // 8])
-        search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8],
-                                                                first_sample_idxs=join() if join else None)
-        template_feature = self._pointwise(self.conv_final, template_feature)
-        search_feature = self._pointwise(self.conv_final, search_feature)
+
+        def template_branch():
+            xyz, feat, idxs = self.backbone(template, [M // 2, M // 4, M // 8])
+            sel = idxs[:, :M // 8, None].expand(-1, -1, self.config.bc_channel).long()
+            return xyz, self._pointwise(self.conv_final, feat), bc_t.gather(dim=1, index=sel)
+
+        if fused is not None and fused.branch_overlap(search):
+            # inference: the two branches are independent up to the cross-correlation -> two streams (two graph branches)
+            join_t = fused.run_ahead(template_branch)
+            search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8])
+            search_feature = self._pointwise(self.conv_final, search_feature)
+            template_xyz, template_feature, template_bc = join_t()
+        else:
+            join = None
+            if self.config.use_fps and fused is not None:
+                join = fused.fps_ahead(search, N // 2)           # search-branch FPS runs underneath the template branch
+            template_xyz, template_feature, template_bc = template_branch()
+            search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8],
+                                                                    first_sample_idxs=join() if join else None)
+            search_feature = self._pointwise(self.conv_final, search_feature)
         pred_search_bc = self._pointwise(self.mlp_bc, torch.cat([search_xyz.transpose(1, 2), search_feature], dim=1))
         pred_search_bc = pred_search_bc.transpose(1, 2)                                   # (B, N//8, 9)
-        sel = sample_idxs_t[:, :M // 8, None].expand(-1, -1, self.config.bc_channel).long()
-        template_bc = template_bc.gather(dim=1, index=sel)
         fusion_feature = self.xcorr(template_feature, search_feature, template_xyz, search_xyz, template_bc,
                                     pred_search_bc)
         estimation_boxes, estimation_cla, vote_xyz, center_xyzs = self.rpn(search_xyz, fusion_feature)

@@ -30,15 +30,27 @@ class P2B(base_model.MatchingBaseModel):
         """input_dict: template_points (B,M,3), search_points (B,N,3) [+ labels]."""
         template, search = input_dict['template_points'], input_dict['search_points']
         M, N = template.shape[1], search.shape[1]
-        join = None
-        if self.config.use_fps and runtime.fused_enabled() and search.is_cuda:
+        fused = None
+        if runtime.fused_enabled() and search.is_cuda:
             from .. import fused
-            join = fused.fps_ahead(search, N // 2)
-        template_xyz, template_feature, _ = self.backbone(template, [M // 2, M // 4, M // 8])
-        search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8],
-                                                                first_sample_idxs=join() if join else None)
-        template_feature = self._pointwise(self.conv_final, template_feature)
-        search_feature = self._pointwise(self.conv_final, search_feature)
+
+        def template_branch():
+            xyz, feat, _ = self.backbone(template, [M // 2, M // 4, M // 8])
+            return xyz, self._pointwise(self.conv_final, feat)
+
+        if fused is not None and fused.branch_overlap(search):
+            join_t = fused.run_ahead(template_branch)        # inference: template branch on the side stream
+            search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8])
+            search_feature = self._pointwise(self.conv_final, search_feature)
+            template_xyz, template_feature = join_t()
+        else:
+            join = None
+            if self.config.use_fps and fused is not None:
+                join = fused.fps_ahead(search, N // 2)
+            template_xyz, template_feature = template_branch()
+            search_xyz, search_feature, sample_idxs = self.backbone(search, [N // 2, N // 4, N // 8],
+                                                                    first_sample_idxs=join() if join else None)
+            search_feature = self._pointwise(self.conv_final, search_feature)
         fusion_feature = self.xcorr(template_feature, search_feature, template_xyz)
         estimation_boxes, estimation_cla, vote_xyz, center_xyzs = self.rpn(search_xyz, fusion_feature)
         return {"estimation_boxes": estimation_boxes, "vote_center": vote_xyz, "pred_seg_score": estimation_cla,

@@ -47,6 +47,19 @@ def set_sa_fused(flag: bool) -> None:
     _SA_FUSED = bool(flag)
 
 
+_BRANCH_OVERLAP = os.environ.get("O3D_BRANCH_OVERLAP", "1") != "0"
+
+
+def branch_overlap_enabled() -> bool:
+    """inference: the template branch runs on a side stream next to the search branch (fused.run_ahead)"""
+    return _BRANCH_OVERLAP
+
+
+def set_branch_overlap(flag: bool) -> None:
+    global _BRANCH_OVERLAP
+    _BRANCH_OVERLAP = bool(flag)
+
+
 _STATIC_WEIGHTS = False
 
 
