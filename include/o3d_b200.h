@@ -347,6 +347,15 @@ int o3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int o3d_crop_box_frame(const float* scans, const long long* count, const long long* frame, const float* center,
                        const float* rot, const float* half, int B, int N, float* local, unsigned char* keep, void* stream);
 
+/* Fixed-shape resampling of a masked candidate set (datasets/points_utils.py:24-40 regularize_pc, device form): per cloud,
+ * n = #keep;  n >= size: the `size` kept candidates with the smallest keys u_perm, in ascending key order (a uniform draw
+ * without replacement);  2 < n < size: draw i = the floor(u_pick[i] * n)-th kept candidate;  n <= 2: zeros.
+ * points [B, N, 3], keep [B, N] (bytes, non-zero = kept), u_perm [B, N] and u_pick [B, size] uniform in [0, 1),
+ * scratch [B, N] int32, out [B, size, 3], src [B, size] int64 (source index of every output point), n_out (nullable) [B] int64.
+ * size <= 2048. */
+int o3d_resample(const float* points, const unsigned char* keep, const float* u_perm, const float* u_pick, int B, int N, int size,
+                 int32_t* scratch, float* out, long long* src, long long* n_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@
 //
 //   warps 0-7: query / gather / epilogue (warp % 4 = the TMEM lane quarter it may read) | 8: MMA issuer, TMEM alloc |
 //   9: weight streamer
+#include <type_traits>
 #include "common.cuh"
 #include "ball_query.cuh"
 #include "tc_ptx.cuh"
@@ -38,6 +39,16 @@ constexpr int SF_MAX_SLOTS = 6;
 constexpr int SF_MISC = 128 + SF_POS * 4 + SF_POS * 16;   // barriers + TMEM slot | idx | rel
 constexpr uint32_t SF_TMEM_COLS = 128;      // two 128-channel tiles x 64 positions
 
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
 struct SfLayer {
     int cout, n_mt, nkb, relu, mma;
     uint32_t vec_off;      // floats from the block start: scale[n_mt * 128] | shift[n_mt * 128]
@@ -52,7 +63,7 @@ struct SfParams {
     SfLayer l[O3D_MAX_LAYERS];
 };
 
-__global__ void __launch_bounds__(SF_THREADS, 1)
+__global__ void __launch_bounds__(SF_THREADS, 2)
     sa_fused_kernel(const SfParams prm, const uint8_t* __restrict__ block, const float* __restrict__ xyz,
                     const float* __restrict__ new_xyz, const float* __restrict__ feat, float* __restrict__ out, int ldo,
                     int32_t* __restrict__ idx_out) {
@@ -200,20 +211,28 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (kb0 + j >= nkb) break;
-                    uint8_t* hi = act + (kb0 + j) * SF_ACT_KB;
-                    uint8_t* lo = hi + SF_ACT_KB / 2;
-                    *reinterpret_cast<float4*>(hi + o0) = hi_part(v0[j]);
-                    *reinterpret_cast<float4*>(lo + o0) = lo_part(v0[j]);
-                    *reinterpret_cast<float4*>(hi + o1) = hi_part(v1[j]);
-                    *reinterpret_cast<float4*>(lo + o1) = lo_part(v1[j]);
+                    const uint32_t hi = o3d_smem_u32(act) + (uint32_t)((kb0 + j) * SF_ACT_KB);
+                    const uint32_t lo = hi + SF_ACT_KB / 2;
+                    sts_v4(hi + o0, hi_part(v0[j]));
+                    sts_v4(lo + o0, lo_part(v0[j]));
+                    sts_v4(hi + o1, hi_part(v1[j]));
+                    sts_v4(lo + o1, lo_part(v1[j]));
                 }
             }
             o3d_fence_proxy_async();
             o3d_mbar_arrive(act_ready);
         }
         // ---- C / D. per layer: accumulators -> (+ coordinate term) -> BatchNorm + ReLU -> next operand | max-pool
+        // (the inner loop is issue-bound — 8 K..16 K outputs per layer on 8 warps — so everything that does not depend on the
+        //  column is hoisted: shared-space addresses with compile-time offsets, the XOR swizzle as 8 per-thread constants,
+        //  shift / mask instead of division by nsample, one instantiation per (first, last, has-MMA) combination)
         const int q = warp & 3, half = warp >> 2;
         const float* vecs = reinterpret_cast<const float*>(block);
+        const uint32_t act_s = o3d_smem_u32(act), rel_s = o3d_smem_u32(s_rel);
+        const int logS = 31 - __clz(S);                 // nsample divides 64: a power of two
+        uint32_t xo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xo[i] = (uint32_t)(((lane >> 2) ^ i) << 4) + (uint32_t)(i * 128);
         int ld_phase = 0;
         for (int l = 0; l < prm.n; ++l) {
             const SfLayer& L = prm.l[l];
@@ -221,59 +240,73 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
             const bool wide = L.n_mt == 2;
             const bool all_cols = wide || S > 32;       // one warp walks all 64 columns (a pooling group never spans two warps)
             const int m = wide ? half : 0;
-            const bool active = wide || S <= 32 || half == 0;
+            const int kb_out = m * 4 + q;               // the k-block of the next operand this warp's 32 channels form
+            // channels past the layer's width are padding: nothing reads them
+            const bool work = (wide || S <= 32 || half == 0) && (last ? kb_out * 32 < L.cout : kb_out < prm.l[l + 1].nkb);
             const int col0 = all_cols ? 0 : half * 32, ncol = all_cols ? 64 : 32;
-            const int chl = m * 128 + q * 32 + lane;    // this thread's output channel
-            const float sc = __ldg(vecs + L.vec_off + chl), sh = __ldg(vecs + L.vec_off + L.n_mt * 128 + chl);
-            float wx0 = 0.f, wx1 = 0.f, wx2 = 0.f;
-            if (l == 0) {
-                const float* wx = vecs + prm.wx_off;
-                const int ldw = L.n_mt * 128;
-                wx0 = __ldg(wx + chl);
-                wx1 = __ldg(wx + ldw + chl);
-                wx2 = __ldg(wx + 2 * ldw + chl);
+            const int chl = kb_out * 32 + lane;         // this thread's output channel
+            float sc = 0.f, sh = 0.f, wx0 = 0.f, wx1 = 0.f, wx2 = 0.f;
+            if (work) {
+                sc = __ldg(vecs + L.vec_off + chl);
+                sh = __ldg(vecs + L.vec_off + L.n_mt * 128 + chl);
+                if (l == 0) {
+                    const float* wx = vecs + prm.wx_off;
+                    const int ldw = L.n_mt * 128;
+                    wx0 = __ldg(wx + chl);
+                    wx1 = __ldg(wx + ldw + chl);
+                    wx2 = __ldg(wx + 2 * ldw + chl);
+                }
             }
+            const float floor_v = L.relu ? 0.f : -INFINITY;
             if (L.mma) {
                 o3d_mbar_wait(layer_done, ld_phase);
                 ld_phase ^= 1;
                 tc_fence_after();
             }
-            if (active) {
-                uint8_t* dst = act + (m * 4 + q) * SF_ACT_KB + (lane & 3) * 4;   // k-block of this warp's 32 channels
-                const int chunk = lane >> 2;
-                float mx = -INFINITY;
-                for (int cc = col0; cc < col0 + ncol; cc += 32) {
-                    uint32_t r[32];
-                    if (L.mma) {
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * SF_POS + cc), r);
-                    } else {
+            if (work) {
+                const uint32_t dst_s = act_s + (uint32_t)(kb_out * SF_ACT_KB + (lane & 3) * 4);
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * SF_POS);
+                const bool out_on = chl < ldo;
+                const bool real = chl < L.cout;
+                auto run = [&](auto first_, auto last_, auto mma_) {
+                    constexpr bool FIRST = decltype(first_)::value, LAST = decltype(last_)::value, MMA = decltype(mma_)::value;
+                    float mx = -INFINITY;
+                    for (int cc = col0; cc < col0 + ncol; cc += 16) {
+                        uint32_t r[16];
+                        if constexpr (MMA) tmem_ld16(t_addr + (uint32_t)cc, r);
+                        const uint32_t rowbase = dst_s + (uint32_t)((cc >> 3) * 1024);
+                        const uint32_t relbase = rel_s + (uint32_t)(cc * 16);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = 0u;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int p = cc + j;
-                        float a = __uint_as_float(r[j]);
-                        if (l == 0) {
-                            const float4 rel = s_rel[p];
-                            a = fmaf(wx2, rel.z, fmaf(wx1, rel.y, fmaf(wx0, rel.x, a)));
-                        }
-                        float v = fmaf(a, sc, sh);
-                        if (L.relu) v = fmaxf(v, 0.f);
-                        if (!last) {
-                            const uint32_t off = sw128(p, chunk);
-                            const float h = hi1(v);
-                            *reinterpret_cast<float*>(dst + off) = h;
-                            *reinterpret_cast<float*>(dst + SF_ACT_KB / 2 + off) = v - h;
-                        } else {
-                            mx = fmaxf(mx, v);
-                            if (((p + 1) % S) == 0) {
-                                const int g = g0 + p / S;
-                                if (g < prm.BM && chl < ldo) out[(size_t)g * ldo + chl] = chl < L.cout ? mx : 0.f;
-                                mx = -INFINITY;
+                        for (int j = 0; j < 16; ++j) {
+                            float a = MMA ? __uint_as_float(r[j]) : 0.f;
+                            if constexpr (FIRST) {
+                                const float4 rel = lds_v4(relbase + j * 16);
+                                a = fmaf(wx2, rel.z, fmaf(wx1, rel.y, fmaf(wx0, rel.x, a)));
+                            }
+                            const float v = fmaxf(fmaf(a, sc, sh), floor_v);
+                            if constexpr (!LAST) {
+                                const uint32_t off = rowbase + (uint32_t)((j >> 3) * 1024) + xo[j & 7];
+                                const float h = hi1(v);
+                                sts_f32(off, h);
+                                sts_f32(off + SF_ACT_KB / 2, v - h);
+                            } else {
+                                mx = fmaxf(mx, v);
+                                if (((cc + j + 1) & (S - 1)) == 0) {
+                                    const int g = g0 + ((cc + j) >> logS);
+                                    if (out_on && g < prm.BM) out[(size_t)g * ldo + chl] = real ? mx : 0.f;
+                                    mx = -INFINITY;
+                                }
                             }
                         }
                     }
+                };
+                using T = std::true_type;
+                using F = std::false_type;
+                if (l == 0) {
+                    if (L.mma) { if (last) run(T{}, T{}, T{}); else run(T{}, F{}, T{}); }
+                    else { if (last) run(T{}, T{}, F{}); else run(T{}, F{}, F{}); }
+                } else {
+                    if (last) run(F{}, T{}, T{}); else run(F{}, F{}, T{});
                 }
             }
             if (!last) {
@@ -371,9 +404,7 @@ bool sf_plan(const o3d_stack_t* d, SfPlan& p) {
         L.mma = L.nkb > 0;
         L.vec_off = (uint32_t)off;
         off += 2 * (size_t)L.n_mt * 128;
-        if (L.nkb > p.max_kb) p.max_kb = L.nkb;
-        // the layer's output becomes the next operand: it fills whole 128-channel tiles, i.e. 4 k-blocks each
-        if (l + 1 < q.n && L.n_mt * 4 > p.max_kb) p.max_kb = L.n_mt * 4;
+        if (L.nkb > p.max_kb) p.max_kb = L.nkb;        // the operand buffer holds the k-blocks a layer reads
     }
     q.wx_off = (uint32_t)off;
     off += 3 * (size_t)q.l[0].n_mt * 128;
@@ -443,17 +474,24 @@ extern "C" int o3d_sa_fused_forward(const o3d_stack_t* d, const void* block, con
     int act = p.max_kb * SF_ACT_KB;
     const int cloud = ((N * 12 + 1023) / 1024) * 1024;
     if (act < cloud) act = cloud;
-    if (act < 32768) act = 32768;
+    if (act < SF_ACT_KB) act = SF_ACT_KB;
     prm.act_bytes = act;
     const int budget = 227 * 1024 - 1024 - SF_MISC - act;
     int nslot = budget / SF_WTILE;
     if (nslot > SF_MAX_SLOTS) nslot = SF_MAX_SLOTS;
+    int tiles = 0;
+    for (int l = 0; l < prm.n; ++l) tiles += prm.l[l].mma ? prm.l[l].n_mt * prm.l[l].nkb : 0;
+    if (nslot > tiles && tiles >= 2) nslot = tiles;       // a short stack needs no deeper ring: leaves room for a second CTA per SM
     O3D_REQUIRE(nslot >= 2, O3D_ERR_ARG, "o3d_sa_fused_forward: N=%d points per cloud do not fit the shared-memory staging", N);
+    const int cpc = SF_POS / nsample;
+    const int grid = (B * M) / cpc;
+    if (grid > o3d_num_sms()) {       // more CTAs than SMs: a shallower ring lets two CTAs share an SM (228 KB, 1 KB reserved per CTA)
+        const int fit = (113 * 1024 - 1024 - SF_MISC - act) / SF_WTILE;
+        if (fit >= 2 && fit < nslot) nslot = fit;
+    }
     prm.nslot = nslot;
     const int smem = 1024 + act + nslot * SF_WTILE + SF_MISC;
     O3D_CUDA(cudaFuncSetAttribute(sa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "o3d_sa_fused_forward: smem attribute");
-    const int cpc = SF_POS / nsample;
-    const int grid = (B * M) / cpc;
     sa_fused_kernel<<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(prm, (const uint8_t*)block, xyz, new_xyz, feat_cl, out, ldo, idx);
     O3D_CHECK_LAUNCH("o3d_sa_fused_forward");
     return O3D_OK;

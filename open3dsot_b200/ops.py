@@ -213,6 +213,28 @@ def p2b_cosine_grad(dsim, sim, tfeat_cl, sfeat_cl, tn, sn, eps=1e-8, need_t=True
 
 
 # ------------------------------------------------------------------ box-frame crop (tracking loop / training sampler)
+RESAMPLE_MAX_SIZE = 2048
+
+
+def resample(points, keep, size, u_perm, u_pick):
+    """Fixed-shape resampling in one kernel (csrc/resample.cu; semantics of tracking/sampling.py): points (B, N, 3) fp32 CUDA,
+    keep (B, N) bool, u_perm (B, N) / u_pick (B, size) uniform [0, 1) -> out (B, size, 3), src (B, size) int64, n (B,) int64."""
+    _chk_f(points, "points")
+    B, N, _ = points.shape
+    keep = keep.contiguous()
+    u_perm, u_pick = u_perm.contiguous(), u_pick.contiguous()
+    assert keep.dtype == torch.bool and keep.shape == (B, N) and u_perm.shape == (B, N) and u_pick.shape == (B, size)
+    assert u_perm.dtype == torch.float32 and u_pick.dtype == torch.float32
+    dev = points.device
+    scratch = torch.empty(B, N, dtype=torch.int32, device=dev)
+    out = torch.empty(B, size, 3, device=dev)
+    src = torch.empty(B, size, dtype=torch.int64, device=dev)
+    n = torch.empty(B, dtype=torch.int64, device=dev)
+    _call("o3d_resample", points.data_ptr(), keep.data_ptr(), u_perm.data_ptr(), u_pick.data_ptr(), B, N, int(size),
+          scratch.data_ptr(), out.data_ptr(), src.data_ptr(), n.data_ptr(), _stream())
+    return out, src, n
+
+
 def crop_box_frame(scans, center, rot, half, frame=None, count=None):
     """scans (F, N, 3) fp32 CUDA; center (B, 3), rot (B, 3, 3), half (B, 3); frame (B,) int64 picks a scan per sample
     (None: sample b reads scan b), count (F,) int64 = valid points per scan.  Returns local (B, N, 3), keep (B, N) bool."""

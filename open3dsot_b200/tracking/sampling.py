@@ -11,6 +11,8 @@ The subset differs from the numpy Generator's (same distribution); tests that co
 the oracle's indices through `indices=`."""
 import torch
 
+from .. import ops, runtime
+
 
 def resample(points, keep, size, generator=None, indices=None, u_perm=None, u_pick=None):
     """points (N, 3), keep (N,) bool -> (size, 3) points, (size,) source indices (into `points`).
@@ -31,8 +33,13 @@ def resample_batched(points, keep, size, u_perm=None, u_pick=None, generator=Non
     with replacement = random ranks mapped to survivors through the running count of the keep-mask."""
     B, n_all = keep.shape
     dev = points.device
-    n = keep.sum(1)
     u = torch.rand(B, n_all, device=dev, generator=generator) if u_perm is None else u_perm
+    if points.is_cuda and points.dtype == torch.float32 and points.shape[-1] == 3 and 3 <= size <= ops.RESAMPLE_MAX_SIZE \
+            and runtime.fused_enabled():
+        # one kernel (csrc/resample.cu): ordered compaction, radix select of the size-th smallest key, sort, gather
+        up = torch.rand(B, size, device=dev, generator=generator) if u_pick is None else u_pick
+        return ops.resample(points.contiguous(), keep, size, u, up)
+    n = keep.sum(1)
     key = torch.where(keep, u, torch.full_like(u, 2.0))
     k = min(size, n_all)
     wo = torch.topk(key, k, dim=1, largest=False, sorted=False).indices
