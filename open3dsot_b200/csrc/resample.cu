@@ -10,7 +10,7 @@
 //   n <= 2        : an all-zero cloud (the reference's "too few points" placeholder).
 // The torch formulation costs ~25 launches (radix top-k over all candidates, cumsum, searchsorted, where / gather glue) —
 // 170 us of a 0.86 ms tracking frame; this is one CTA per cloud:
-//   A. ordered compaction of the kept indices (block scan, 4 candidates per thread and round),
+//   A. ordered compaction of the kept indices (a contiguous run of candidates per thread, one block scan),
 //   B. 3-pass radix select (11 / 11 / 10 bits, shared-memory histograms) of the size-th smallest key over the survivors,
 //   C. collection of the keys below the threshold (+ ties in index order), bitonic sort of the <= 2048 (key, index) pairs,
 //   D. gather of the selected points.
@@ -64,20 +64,33 @@ __global__ void __launch_bounds__(RS_THREADS)
     float* __restrict__ O = out + (size_t)b * size * 3;
     long long* __restrict__ SRC = src + (size_t)b * size;
 
-    // ---- A. ordered compaction of the kept indices
-    uint32_t n = 0;
-    for (int c0 = 0; c0 < N; c0 += RS_THREADS * 4) {
-        const int i0 = c0 + tid * 4;
+    // ---- A. ordered compaction of the kept indices: every thread owns a CONTIGUOUS run of candidates (one block scan in all;
+    //         the flags are read twice — count, then write — the second time from L1)
+    const int L = (((N + RS_THREADS - 1) / RS_THREADS) + 3) & ~3;
+    const int beg = tid * L, end = min(N, beg + L);
+    const bool vec = (reinterpret_cast<uintptr_t>(K) & 3) == 0;
+    auto flags4 = [&](int i) -> uint32_t {             // bit j set = candidate i + j is kept
         uint32_t f = 0;
+        if (vec && i + 4 <= N) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(K + i);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f |= ((w >> (8 * j)) & 0xFFu) ? 1u << j : 0u;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i + j < N && K[i + j]) f |= 1u << j;
+        }
+        return f;
+    };
+    uint32_t cnt = 0;
+    for (int i = beg; i < end; i += 4) cnt += __popc(flags4(i));
+    uint32_t n;
+    uint32_t pos = block_exscan(cnt, s_warp, n);
+    for (int i = beg; i < end; i += 4) {
+        const uint32_t f = flags4(i);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (i0 + j < N && K[i0 + j]) f |= 1u << j;
-        uint32_t total;
-        uint32_t pos = n + block_exscan(__popc(f), s_warp, total);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (f & (1u << j)) S[pos++] = i0 + j;
-        n += total;
+            if (f & (1u << j)) S[pos++] = i + j;
     }
     __syncthreads();                       // S (global) written by this block, read below by other threads of it
     if (tid == 0 && n_out) n_out[b] = n;

@@ -152,7 +152,8 @@ bool make_plan(const o3d_stack_t* d, Plan& p) {
         // forward: also single, partly filled position tiles (P >= 16: the B = 1 tracking frame's 64 / 128-position head layers —
         // on the CUDA-core kernel such a layer is a 256-deep serial loop on two CTAs, 38 us; here one tile, 15 us)
         // (inference: also narrow output layers — 1 / 5 / 9 channels of the heads — as one partly filled channel tile)
-        p.tc_f[l] = (d->use_tc & 1) && (p.Nw[l] % 128 == 0 || p.Nw[l] == 64 || (!d->training && p.Nw[l] < 128)) && p.K[l] >= 32 &&
+        // (inference: any output width — e.g. the vote layer's 3 + 256 channels — as whole + one partly filled channel tile)
+        p.tc_f[l] = (d->use_tc & 1) && (p.Nw[l] % 128 == 0 || p.Nw[l] == 64 || !d->training) && p.K[l] >= 32 &&
                     d->P >= (d->training ? 128 : 16) &&
                     !(l == d->n_layers - 1 && d->S > 0 && 64 % d->S != 0);
         p.tc_b[l] = (d->use_tc & 1) && p.K[l] >= 64 && p.Nw[l] >= 32 && d->P >= 128;
