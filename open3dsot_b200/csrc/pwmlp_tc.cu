@@ -1109,6 +1109,7 @@ __global__ void w_pretile_kernel(const float* __restrict__ W, int ld, int rows, 
 int g_tc_debug = 0, g_tc_force_mt = 0;
 }  // namespace
 extern int o3d_g_fps_wide;
+extern int o3d_g_sa_fused_dbg;
 namespace {
 inline int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 thread_local int g_tc_rev = 0;   // direction of the next launch (set by the stack sequencer)
@@ -1184,6 +1185,7 @@ extern "C" void o3d_debug_set(int tc_debug, int force_mt) {
     g_tc_force_mt = force_mt;
     o3d_g_no_skinny = (tc_debug & 128) != 0;
     o3d_g_fps_wide = (tc_debug & 1024) != 0;
+    o3d_g_sa_fused_dbg = (tc_debug >> 11) & 15;
 }
 extern "C" void o3d_pw_tc_set_reverse(int rev) { g_tc_rev = rev; }
 
