@@ -405,7 +405,7 @@ def _sa_fused_block(d, params, bns, device):
         _lib.check(L.o3d_sa_fused_prepare(ctypes.byref(d), block.data_ptr(), _stream()), "o3d_sa_fused_prepare")
         return block
 
-    if not runtime.static_weights() or not _cacheable():
+    if not runtime.static_weights():
         return make()
     stats = [t for bn in bns if bn is not None for t in (bn.running_mean, bn.running_var)]
     owner = params[0]
@@ -414,6 +414,8 @@ def _sa_fused_block(d, params, bns, device):
     ver = _versions(params) + _versions(stats)
     hit = cache.get(key)
     if hit is None or hit[0] != ver:
+        if not _cacheable():
+            return make()                                 # during graph capture: built privately, as part of the graph
         hit = cache[key] = (ver, make(), params, stats)
         _publish()
     return hit[1]
