@@ -288,7 +288,7 @@ int o3d_stack_backward(const o3d_stack_t* d, const float* x, const void* ws_fwd,
  * body of _PointnetSAModuleBase.forward — QueryAndGroup (pointnet2/utils/pointnet2_utils.py:299-339), the SharedMLP and the
  * max-pool over nsample (pointnet2/utils/pointnet2_modules.py:58-76) — for one (grouper, mlp) scale.
  * d describes the SharedMLP in the reference's layout: xyz_first = 1, c0 = feature channels C, cin[0] = 3 + C, every cout <= 256,
- * C <= 256; P / K0 / S / training / lift are ignored.  o3d_sa_fused_prepare() packs the weights (pre-tiled TF32 hi | lo images) and
+ * C <= 288; P / K0 / S / training / lift are ignored.  o3d_sa_fused_prepare() packs the weights (pre-tiled TF32 hi | lo images) and
  * folds BatchNorm + bias into per-channel scale / shift once; `block` (o3d_sa_fused_prepared_bytes() bytes) then serves every call.
  * xyz [B, N, 3], new_xyz [B, M, 3], feat_cl [B, N, ldf] channels-last (NULL iff c0 == 0), out [B * M, ldo] channels-last,
  * idx (nullable) [B, M, nsample] receives the ball-query result.  nsample must divide 64 and M be a multiple of 64 / nsample. */

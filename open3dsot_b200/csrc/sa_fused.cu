@@ -399,7 +399,7 @@ bool sf_plan(const o3d_stack_t* d, SfPlan& p) {
     SfParams& q = p.prm;
     q.n = d->n_layers;
     const int C = d->c0;
-    if (d->cin[0] != C + 3 || C > 256) return false;
+    if (d->cin[0] != C + 3 || C > 288) return false;     // 9 k-blocks of input features: 144 KB operand + a two-slot weight ring
     q.Cp = (C + 3) & ~3;
     size_t off = 0;   // floats
     p.max_kb = 0;

@@ -382,7 +382,7 @@ def _sa_fused_ok(specs, S, npoint, N, C):
     """shape range of o3d_sa_fused_forward (csrc/sa_fused.cu): nsample | 64, <= 256 channels per layer, BatchNorm with running stats"""
     if not runtime.sa_fused_enabled() or runtime.CHOICE_HOOK is not None or not runtime.fused_enabled():
         return False
-    if S < 1 or 64 % S != 0 or npoint % (64 // S) != 0 or C > 256 or N * 12 > 96 * 1024 or len(specs) > _lib.MAX_LAYERS:
+    if S < 1 or 64 % S != 0 or npoint % (64 // S) != 0 or C > 288 or N * 12 > 96 * 1024 or len(specs) > _lib.MAX_LAYERS:
         return False
     for s in specs:
         if s.weight is None or s.weight.shape[0] > 256:

@@ -32,10 +32,17 @@ class P2BVoteNetRPN(nn.Module):
             mlp = fused.seq_forward
         else:
             mlp = lambda m, x: m(x)  # noqa: E731
-        estimation_cla = mlp(self.FC_layer_cla, feature).squeeze(1)
-        score = estimation_cla.sigmoid()
+        join_cla = None
+        if runtime.fused_enabled() and fused.branch_overlap(feature):
+            # inference: the seed classifier and the vote layer read the same features and meet only at the vote clustering
+            join_cla = fused.run_ahead(lambda: mlp(self.FC_layer_cla, feature).squeeze(1))
+        else:
+            estimation_cla = mlp(self.FC_layer_cla, feature).squeeze(1)
         xyz_feature = torch.cat((xyz.transpose(1, 2), feature), dim=1)
         vote = xyz_feature + mlp(self.vote_layer, xyz_feature)
+        if join_cla is not None:
+            estimation_cla = join_cla()
+        score = estimation_cla.sigmoid()
         vote_xyz = vote[:, 0:3, :].transpose(1, 2).contiguous()
         vote_feature = torch.cat((score.unsqueeze(1), vote[:, 3:, :]), dim=1)
         center_xyzs, proposal_features = self.vote_aggregation(vote_xyz, vote_feature, self.num_proposal)

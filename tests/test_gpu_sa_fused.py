@@ -80,6 +80,7 @@ CASES = [
     ("empty_balls", 2, 64, 12, [12, 33, 20, 9], 32, 0.01, 8, False),         # most balls hold only the centre itself / nothing
     ("one_layer_wide", 2, 80, 40, [40, 200], 16, 0.5, 64, False),            # nsample 64: one centre per CTA, single layer
     ("nsample_4", 2, 70, 0, [0, 24, 48], 32, 0.3, 4, False),
+    ("vote_aggregation", 2, 128, 257, [257, 256, 256, 256], 64, 0.3, 16, True),   # the RPN's cluster layer: 9 input k-blocks
 ]
 
 
