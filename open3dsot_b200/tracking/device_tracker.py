@@ -98,28 +98,40 @@ class DeviceTracker:
         if self.motion:
             return self._inputs_motion()
         cfg, box = self.cfg, self._box()
-        # search area: current scan in the frame of the reference box (= previous result)
         b1 = bx.Box(box.center[None], box.wlh[None], box.rot[None])
+
+        def build_template():
+            # template: first-frame crop (+ previous-frame crop around the previous result)
+            mode = cfg.shape_aggregation.upper()
+            p_local, p_keep = bx.crop_in_box_frame(self.prev_scan[None], b1, cfg.model_bb_scale, cfg.model_bb_offset)
+            p_local, p_keep = p_local[0], p_keep[0] & self.prev_valid
+            if "FIRSTANDPREVIOUS" in mode:
+                cand, keep = torch.cat([self.first_local, p_local]), torch.cat([self.first_keep, p_keep])
+            elif "FIRST" in mode:
+                cand, keep = self.first_local, self.first_keep
+            elif "PREVIOUS" in mode:
+                cand, keep = p_local, p_keep
+            else:
+                raise NotImplementedError(f"shape_aggregation '{cfg.shape_aggregation}' needs every past frame on the device")
+            template, _ = resample(cand, keep, cfg.template_size, u_perm=self.u_t[0][: cand.shape[0]], u_pick=self.u_t[1])
+            bc = None
+            if self.needs_bc:
+                canon = bx.Box(torch.zeros_like(box.center), box.wlh, torch.eye(3, device=self.dev))
+                bc = bx.point_to_box_distance(template, canon)[None]
+            return template[None], bc
+
+        from .. import fused
+        # the two crops + draws are independent: the template's run on the side stream (a parallel branch of the frame's graph)
+        overlap = fused.branch_overlap(self.scan)
+        join = fused.run_ahead(build_template) if overlap else None
+        # search area: current scan in the frame of the reference box (= previous result)
         s_local, s_keep = bx.crop_in_box_frame(self.scan[None], b1, cfg.search_bb_scale, cfg.search_bb_offset)
         s_local, s_keep = s_local[0], s_keep[0]
         search, _ = resample(s_local, s_keep & self.scan_valid, cfg.search_size, u_perm=self.u_s[0], u_pick=self.u_s[1])
-        # template: first-frame crop (+ previous-frame crop around the previous result)
-        mode = cfg.shape_aggregation.upper()
-        p_local, p_keep = bx.crop_in_box_frame(self.prev_scan[None], b1, cfg.model_bb_scale, cfg.model_bb_offset)
-        p_local, p_keep = p_local[0], p_keep[0] & self.prev_valid
-        if "FIRSTANDPREVIOUS" in mode:
-            cand, keep = torch.cat([self.first_local, p_local]), torch.cat([self.first_keep, p_keep])
-        elif "FIRST" in mode:
-            cand, keep = self.first_local, self.first_keep
-        elif "PREVIOUS" in mode:
-            cand, keep = p_local, p_keep
-        else:
-            raise NotImplementedError(f"shape_aggregation '{cfg.shape_aggregation}' needs every past frame on the device")
-        template, _ = resample(cand, keep, cfg.template_size, u_perm=self.u_t[0][: cand.shape[0]], u_pick=self.u_t[1])
-        data = {"template_points": template[None], "search_points": search[None]}
-        if self.needs_bc:
-            canon = bx.Box(torch.zeros_like(box.center), box.wlh, torch.eye(3, device=self.dev))
-            data["points2cc_dist_t"] = bx.point_to_box_distance(template, canon)[None]
+        template, bc = join() if overlap else build_template()
+        data = {"template_points": template, "search_points": search[None]}
+        if bc is not None:
+            data["points2cc_dist_t"] = bc
         return data
 
     def _frame(self):
