@@ -32,7 +32,7 @@ def _cloud(B, N, seed, spread=1.2):
     return xyz, g
 
 
-def _module(mlp, radius, nsample, seed, normalize=False):
+def _module(mlp, radius, nsample, seed, normalize=False, device="cuda"):
     sa = PointnetSAModule(mlp=list(mlp), radius=radius, nsample=nsample, use_fps=False, normalize_xyz=normalize)
     sa.load_state_dict(det_state_dict(sa.state_dict(), seed=seed))
     g = torch.Generator().manual_seed(seed + 100)
@@ -41,14 +41,17 @@ def _module(mlp, radius, nsample, seed, normalize=False):
             b.copy_(torch.randn(b.shape, generator=g) * 0.3)
         elif n.endswith("running_var"):
             b.copy_(torch.rand(b.shape, generator=g) * 1.5 + 0.25)
-    return sa.cuda().eval()
+    return sa.to(device).eval()
 
 
-def _reference64(sa, xyz, feats, npoint):
-    """float64 composition on the kernel-exact neighbour indices"""
+def _reference64(sa, xyz, feats, npoint, idx=None):
+    """float64 composition on the kernel-exact neighbour indices (`idx`: indices from elsewhere — tests/test_oracle_sa_eval.py
+    feeds the CPU oracle's to show that this yardstick and the pinned oracle are the same function)"""
     grouper = sa.groupers[0]
     new_xyz = xyz[:, :npoint].contiguous()
-    idx = ops.ball_query(new_xyz, xyz, grouper.radius, grouper.nsample).long()        # (B, npoint, S)
+    if idx is None:
+        idx = ops.ball_query(new_xyz, xyz, grouper.radius, grouper.nsample)
+    idx = idx.long()                                                                     # (B, npoint, S)
     B, M, S = idx.shape
     g_xyz = (xyz.unsqueeze(1).expand(-1, M, -1, -1).gather(2, idx.unsqueeze(-1).expand(-1, -1, -1, 3))
              - new_xyz.unsqueeze(2)).double()               # the fp32 difference, as the reference forms it
